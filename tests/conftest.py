@@ -1,0 +1,25 @@
+import gzip
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_bundle():
+    path = os.path.join(ROOT, "tests", "golden", "sanity_fixtures.json.gz")
+    with gzip.open(path, "rb") as f:
+        return json.loads(f.read().decode())
+
+
+@pytest.fixture(scope="session")
+def bundle():
+    return load_bundle()
