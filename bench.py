@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- pivots/sec on the synthetic dense 2000x2000 fp64 LP (BASELINE.json configs[2]).
+
+A "step" is one complete `Tableau.simplex()` of the 2001x2001 tableau (phase 1 + phase 2, about
+8k pivots under the reference's partial-pricing rule).  `value` = pivots/s with the initial
+tableau already resident in HBM (each step restores it device-to-device, then solves);
+`e2e` = the same solve through the reference-facing call with HOST buffers: H2D upload of the
+tableau from pinned memory, solve, D2H read-back of the RHS column and basis arrays, all inside
+the timed region.  L2 is flushed between timed steps (the 32 MB tableau is smaller than L2; inside
+a step the tableau legitimately stays L2-resident because every pivot rewrites all of it).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle restatement of the
+        reference's TypeScript path (Node.js is not available), single thread, bounded sample.
+
+LP does not shard (SURVEY.md 8e "replicas only"): with N > 1 every rank solves its own replica
+and `value` is the aggregate (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pivots_per_sec_dense_lp_2000x2000_fp64"
+UNIT = "pivots/s"
+
+
+def algorithmic_bytes_per_pivot(H: int, W: int) -> int:
+    """read+write every element, pricing scan, ratio test, row/column staging."""
+    return 16 * H * W + 8 * W + 16 * H + 8 * (H + W)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(it, pivots: int):
+    """The reference's CPU path restated (oracle/, single thread) on the first `pivots` pivots."""
+    from oracle import ref_model
+    t = ref_model.OracleTableau(it.matrix, it.varIndexByRow, it.varIndexByCol, check_cycles=True, fast_cycles=False)
+    t.set_pivot_limit(pivots)
+    t0 = time.perf_counter()
+    st = t.simplex()
+    dt = time.perf_counter() - t0
+    return st.totalPivots, dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from jslpsolver_b200 import problems
+    it = problems.dense_packing_lp_tableau(args.size, args.size, args.seed)
+    sample = args.cpu_pivots
+    for _ in range(args.warmup):
+        cpu_sample(it, max(10, sample // 10))
+    tot_p, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        p, dt = cpu_sample(it, sample)
+        tot_p += p
+        tot_t += dt
+    value = tot_p / tot_t
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"first {sample} pivots of the same {args.size}x{args.size} solve per step; "
+                                   f"oracle/ C restatement of the reference's single-threaded TypeScript path "
+                                   f"(no Node.js on this image); box has {cores} host cores, the reference can use 1"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    n = args.size
+    return {"workload": f"synthetic dense packing LP {n}x{n} fp64 (tableau {n + 1}x{n + 1}, seed {args.seed}, "
+                        f"a~U{{1..20}}, b~U{{100..500}}, c~U{{1..50}}), BASELINE.json configs[2]; one step = one full "
+                        f"simplex() solve",
+            "l2": "flushed between timed steps (256 MiB write); tableau is L2-resident within a solve",
+            "parallelism": "replicas (LP does not shard)", "check_cycles": True}
+
+
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from jslpsolver_b200 import _lib, problems
+    from jslpsolver_b200.tableau import DeviceContext, GpuTableau
+
+    # one explicit stream for everything: the library launches on it, torch events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = DeviceContext(local_rank, stream.cuda_stream)
+    it = problems.dense_packing_lp_tableau(args.size, args.size, args.seed)
+    H, W = it.matrix.shape
+    # pinned host buffers: the e2e arm uploads from these every step
+    pin_M = torch.from_numpy(it.matrix).pin_memory()
+    pin_vr = torch.from_numpy(it.varIndexByRow).pin_memory()
+    pin_vc = torch.from_numpy(it.varIndexByCol).pin_memory()
+    g = GpuTableau(1e-8, context=ctx)
+    g.upload(pin_M.numpy(), pin_vr.numpy(), pin_vc.numpy(), row_capacity=H)
+    if args.engine:
+        g.set_option(_lib.OPT_ENGINE, args.engine)
+    if args.batch:
+        g.set_option(_lib.OPT_BATCH, args.batch)
+    g.save()  # device-resident initial tableau
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        g.restore()
+        g.simplex()
+        return g.lastStatus
+
+    out_rhs = torch.empty(H, dtype=torch.float64).pin_memory()
+    out_vr = torch.empty(H, dtype=torch.int32).pin_memory()
+    out_vc = torch.empty(W, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        L = ctx.lib
+        _lib.check(L.jslp_tab_upload(g.handle, pin_M.data_ptr(), pin_vr.data_ptr(), pin_vc.data_ptr(), None, W + H - 2,
+                                     None, 0, 0, None))
+        g.simplex()
+        _lib.check(L.jslp_download(g.handle, None, out_rhs.data_ptr(), None, out_vr.data_ptr(), out_vc.data_ptr(),
+                                   None, None, None))
+        return g.lastStatus
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    ms, pivots, solve_ms = 0.0, 0, 0.0
+    last = None
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed steps (outside the timed events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = step_resident()
+        e1.record(stream)
+        e1.synchronize()
+        ms += e0.elapsed_time(e1)
+        solve_ms += last.gpu_ms
+        pivots += last.phase1_pivots + last.phase2_pivots
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    barrier()
+
+    # e2e: host buffers in, host buffers out, copies inside the timed region
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e_ms, e_pivots = 0.0, 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = step_e2e()
+        e1.record(stream)
+        e1.synchronize()
+        e_ms += e0.elapsed_time(e1)
+        e_pivots += st.phase1_pivots + st.phase2_pivots
+    barrier()
+
+    t = torch.tensor([ms, e_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([pivots, e_pivots, launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, e_ms_max = t.tolist()
+    tot_pivots, tot_e_pivots, tot_launches = cnt.tolist()
+
+    if rank == 0:
+        value = tot_pivots / (ms_max * 1e-3)
+        e2e_value = tot_e_pivots / (e_ms_max * 1e-3)
+        peak, peak_src = measured_peak()
+        bpp = algorithmic_bytes_per_pivot(H, W)
+        # dominant kernel = k_pivot_step, one launch per pivot: average launch duration over the
+        # event-timed solve region of this rank (launch gaps and the host polls are inside it, so
+        # this is a conservative per-launch figure)
+        per_launch_us = 1e3 * ms / max(1, pivots)
+        achieved = bpp / (per_launch_us * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "pivots_per_step": pivots / args.steps,
+            "final": {"feasible": bool(last.feasible), "bounded": bool(last.bounded), "evaluation": last.evaluation,
+                      "phase1_pivots": last.phase1_pivots, "phase2_pivots": last.phase2_pivots,
+                      "engine": last.engine},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_pivot_step",
+                         "bytes_per_launch": bpp, "avg_launch_us": per_launch_us,
+                         "note": "32 MB tableau < 126 MB L2: DRAM traffic per launch is below the algorithmic "
+                                 "bytes; see profiles/ for the ncu dram__bytes figures"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(H * W * 8 + (H + W) * 4),
+                    "d2h_bytes_per_step": int(H * 8 + (H + W) * 4), "ms_per_step": e_ms_max / args.steps},
+            "gpu_launches": int(tot_launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            p, dt = cpu_sample(it, args.cpu_pivots)
+            line["cpu_baseline"] = {
+                "value": p / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"first {p} pivots of the same solve ({dt:.1f} s); oracle/ C restatement, 1 thread "
+                          f"(the reference is single-threaded; box has {os.cpu_count()} host cores)"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=2000)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--cpu-pivots", type=int, default=1500)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,751 @@
+// jslpsolver_b200/csrc/jslp_api.cu -- C ABI (include/jslp_b200.h) over the sm_100a kernels.
+//
+// Host-side responsibilities (everything else is on the device):
+//   * tableau storage management (padded rows, growth on addCutConstraints)
+//   * enqueueing batches of pivot steps as CUDA graphs and polling the pivot record
+//   * checkForCycles (simplex.ts:415-440) over the drained pivot log, with snapshot + replay so
+//     the final state is the one the reference stops in (it stops BEFORE the repeating pivot)
+//   * setEvaluation rounding (tableau.ts:420-430) and the Tableau flag contract
+//   * the branch-and-cut frontier (branch-and-cut.ts:54-199, min-heap.ts) -- see jslp_bnb.cuh
+#include "../../include/jslp_b200.h"
+#include "jslp_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace jslp;
+
+static thread_local std::string g_err = "";
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(JSLP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct jslp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int num_sms = 148;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct Saved {
+    bool valid = false;
+    int H = 0, nVars = 0, lastElementIndex = 0;
+    double *M = nullptr;
+    int *vrow = nullptr, *vcol = nullptr;
+    double *opt = nullptr;
+    int rowcap = 0;
+};
+
+struct Snapshot {  // per-batch restart point for cycle rewind
+    double *M = nullptr, *opt = nullptr, *prow = nullptr, *pcol = nullptr, *optcoef = nullptr;
+    int *vrow = nullptr, *vcol = nullptr;
+    Rec *rec = nullptr;
+    int rowcap = 0;
+};
+
+struct NodeLogEntry {
+    double v[8];
+};
+
+struct jslp_tab {
+    jslp_ctx *ctx = nullptr;
+    TabDev hd{};            // host mirror of the device descriptor
+    TabDev *d_T = nullptr;
+    Rec *d_rec = nullptr;
+    Rec *h_rec = nullptr;   // pinned
+    int4 *h_log = nullptr;  // pinned, plog_cap entries
+    MipOut *d_mip = nullptr, *h_mip = nullptr;
+    CutDev *d_cuts = nullptr;
+    CutDev *h_cuts = nullptr;
+    int cuts_cap = 0;
+    int W = 0, H = 0, rowcap = 0, stride = 0, nOpt = 0, n_index = 0, n_int = 0;
+    double precision = 1e-8;
+    // Tableau scalar state (tableau.ts:59-92)
+    int feasible = 1, bounded = 1, simplexIters = 0, unboundedVar = -1;
+    int nVars = 0, lastElementIndex = 0;
+    double evaluation = 0, bestPossibleEval = 0;
+    int isIntegralFlag = 0, bncIterations = 0;
+    // options
+    int engine = 0, batch = 256;
+    int64_t host_log_cap = 0;
+    std::vector<int4> host_log;
+    // graphs
+    cudaGraphExec_t g_fused = nullptr, g_simple = nullptr;
+    int g_batch = 0, g_grid = 0, g_smem = 0;
+    Saved saved;
+    Snapshot snap;
+    std::vector<NodeLogEntry> node_log;
+};
+
+extern "C" const char *jslp_last_error(void) { return g_err.c_str(); }
+extern "C" int jslp_abi_version(void) { return 1; }
+
+extern "C" int jslp_ctx_create(int device, void *stream, jslp_ctx **out) {
+    if (!out) return fail(JSLP_E_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(JSLP_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                     " (libjslp_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(JSLP_E_INVALID, "bad device ordinal");
+    CK(cudaSetDevice(device));
+    jslp_ctx *c = new jslp_ctx();
+    c->device = device;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    c->num_sms = p.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+    }
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return JSLP_OK;
+}
+
+extern "C" void jslp_ctx_destroy(jslp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" void *jslp_ctx_stream(jslp_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int64_t jslp_ctx_launches(jslp_ctx *c) { return c ? c->launches : 0; }
+extern "C" int jslp_ctx_sync(jslp_ctx *c) {
+    if (!c) return fail(JSLP_E_INVALID, "ctx is NULL");
+    CK(cudaStreamSynchronize(c->stream));
+    return JSLP_OK;
+}
+
+static void drop_graphs(jslp_tab *t) {
+    if (t->g_fused) cudaGraphExecDestroy(t->g_fused);
+    if (t->g_simple) cudaGraphExecDestroy(t->g_simple);
+    t->g_fused = t->g_simple = nullptr;
+}
+
+static int push_desc(jslp_tab *t) {
+    t->hd.W = t->W; t->hd.H = t->H; t->hd.stride = t->stride; t->hd.rowcap = t->rowcap;
+    t->hd.nOpt = t->nOpt; t->hd.n_index = t->n_index; t->hd.prec = t->precision;
+    CK(cudaMemcpyAsync(t->d_T, &t->hd, sizeof(TabDev), cudaMemcpyHostToDevice, t->ctx->stream));
+    // the source is a pageable host struct: the runtime stages it before returning
+    return JSLP_OK;
+}
+
+static int alloc_rows(jslp_tab *t, int rowcap) {
+    // (re)allocates every buffer whose size depends on the row capacity, preserving contents
+    double *M = nullptr, *pcol = nullptr;
+    int *vrow = nullptr;
+    CK(cudaMalloc(&M, sizeof(double) * (size_t)rowcap * t->stride));
+    CK(cudaMalloc(&pcol, sizeof(double) * (size_t)rowcap));
+    CK(cudaMalloc(&vrow, sizeof(int) * (size_t)rowcap));
+    cudaStream_t s = t->ctx->stream;
+    CK(cudaMemsetAsync(M, 0, sizeof(double) * (size_t)rowcap * t->stride, s));
+    CK(cudaMemsetAsync(pcol, 0, sizeof(double) * (size_t)rowcap, s));
+    CK(cudaMemsetAsync(vrow, 0xff, sizeof(int) * (size_t)rowcap, s));
+    if (t->hd.M) {
+        CK(cudaMemcpyAsync(M, t->hd.M, sizeof(double) * (size_t)t->H * t->stride, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(vrow, t->hd.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        cudaFree(t->hd.M); cudaFree(t->hd.pcol); cudaFree(t->hd.vrow);
+    }
+    t->hd.M = M; t->hd.pcol = pcol; t->hd.vrow = vrow;
+    t->rowcap = rowcap;
+    return JSLP_OK;
+}
+
+extern "C" int jslp_tab_create(jslp_ctx *ctx, int width, int height, int row_capacity, double precision,
+                               jslp_tab **out) {
+    if (!ctx || !out) return fail(JSLP_E_INVALID, "ctx/out is NULL");
+    if (width < 1 || height < 1) return fail(JSLP_E_INVALID, "width/height must be >= 1");
+    if (row_capacity < height) row_capacity = height;
+    CK(cudaSetDevice(ctx->device));
+    jslp_tab *t = new jslp_tab();
+    t->ctx = ctx;
+    t->W = width; t->H = height; t->precision = precision;
+    t->stride = (width + 15) & ~15;  // rows start on 128-byte lines; index math keeps the logical W
+    if ((size_t)t->stride * 8 > 200 * 1024) {
+        delete t;
+        return fail(JSLP_E_CAPACITY, "width exceeds the shared-memory pivot-row staging limit (25600 columns)");
+    }
+    t->n_index = width + height - 2;
+    t->nVars = t->n_index;
+    t->lastElementIndex = t->n_index;
+    int rc = alloc_rows(t, row_capacity);
+    if (rc) { delete t; return rc; }
+    CK(cudaMalloc(&t->hd.vcol, sizeof(int) * (size_t)width));
+    CK(cudaMalloc(&t->hd.prow, sizeof(double) * (size_t)t->stride));
+    CK(cudaMalloc(&t->hd.optflag, (size_t)width));
+    t->hd.plog_cap = 4096;
+    CK(cudaMalloc(&t->hd.plog, sizeof(int4) * (size_t)t->hd.plog_cap));
+    CK(cudaMalloc(&t->d_T, sizeof(TabDev)));
+    CK(cudaMalloc(&t->d_rec, sizeof(Rec)));
+    CK(cudaMalloc(&t->d_mip, sizeof(MipOut)));
+    CK(cudaMallocHost(&t->h_rec, sizeof(Rec)));
+    CK(cudaMallocHost(&t->h_log, sizeof(int4) * (size_t)t->hd.plog_cap));
+    CK(cudaMallocHost(&t->h_mip, sizeof(MipOut)));
+    CK(cudaMemsetAsync(t->d_rec, 0, sizeof(Rec), ctx->stream));
+    CK(cudaMemsetAsync(t->hd.prow, 0, sizeof(double) * (size_t)t->stride, ctx->stream));
+    // phase-2 partial pricing parameters (simplex.ts:118-127)
+    const int nColumns = width - 1;
+    int bs = (int)std::floor(std::sqrt((double)nColumns));
+    bs = std::min(500, std::max(50, bs));
+    t->hd.batch_size = bs;
+    t->hd.use_partial = nColumns > bs * 2;
+    rc = push_desc(t);
+    if (rc) { delete t; return rc; }
+    *out = t;
+    return JSLP_OK;
+}
+
+static void free_saved(Saved &s) {
+    cudaFree(s.M); cudaFree(s.vrow); cudaFree(s.vcol); cudaFree(s.opt);
+    s = Saved();
+}
+static void free_snap(Snapshot &s) {
+    cudaFree(s.M); cudaFree(s.opt); cudaFree(s.prow); cudaFree(s.pcol); cudaFree(s.optcoef);
+    cudaFree(s.vrow); cudaFree(s.vcol); cudaFree(s.rec);
+    s = Snapshot();
+}
+
+extern "C" void jslp_tab_destroy(jslp_tab *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    drop_graphs(t);
+    cudaFree(t->hd.M); cudaFree(t->hd.vrow); cudaFree(t->hd.vcol); cudaFree(t->hd.unres);
+    cudaFree(t->hd.opt); cudaFree(t->hd.prow); cudaFree(t->hd.pcol); cudaFree(t->hd.optcoef);
+    cudaFree(t->hd.plog); cudaFree(t->hd.optflag); cudaFree(t->hd.intpos);
+    cudaFree(t->d_T); cudaFree(t->d_rec); cudaFree(t->d_mip); cudaFree(t->d_cuts);
+    cudaFreeHost(t->h_rec); cudaFreeHost(t->h_log); cudaFreeHost(t->h_mip); cudaFreeHost(t->h_cuts);
+    free_saved(t->saved);
+    free_snap(t->snap);
+    delete t;
+}
+
+extern "C" int jslp_tab_upload(jslp_tab *t, const double *matrix, const int32_t *vrow, const int32_t *vcol,
+                               const uint8_t *unrestricted, int n_index, const int32_t *int_vars, int n_int,
+                               int n_opt, const double *opt_obj) {
+    if (!t || !matrix || !vrow || !vcol) return fail(JSLP_E_INVALID, "NULL argument");
+    if (n_opt < 0 || n_int < 0) return fail(JSLP_E_INVALID, "negative count");
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    CK(cudaMemcpy2DAsync(t->hd.M, sizeof(double) * t->stride, matrix, sizeof(double) * t->W,
+                         sizeof(double) * t->W, t->H, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vrow, vrow, sizeof(int) * t->H, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vcol, vcol, sizeof(int) * t->W, cudaMemcpyHostToDevice, s));
+    if (n_index > 0) t->n_index = n_index;
+    cudaFree(t->hd.unres); t->hd.unres = nullptr;
+    bool any_unres = false;
+    if (unrestricted) for (int i = 0; i < t->n_index; i++) any_unres |= unrestricted[i] != 0;
+    if (any_unres) {
+        CK(cudaMalloc(&t->hd.unres, (size_t)t->n_index));
+        CK(cudaMemcpyAsync(t->hd.unres, unrestricted, (size_t)t->n_index, cudaMemcpyHostToDevice, s));
+    }
+    cudaFree(t->hd.intpos); t->hd.intpos = nullptr;
+    t->n_int = n_int;
+    if (n_int > 0) {
+        if (!int_vars) return fail(JSLP_E_INVALID, "int_var_indices is NULL");
+        std::vector<int> pos((size_t)t->n_index, -1);
+        for (int i = 0; i < n_int; i++) {
+            if (int_vars[i] < 0 || int_vars[i] >= t->n_index) return fail(JSLP_E_INVALID, "integer var index out of range");
+            if (pos[int_vars[i]] < 0) pos[int_vars[i]] = i;
+        }
+        CK(cudaMalloc(&t->hd.intpos, sizeof(int) * (size_t)t->n_index));
+        CK(cudaMemcpyAsync(t->hd.intpos, pos.data(), sizeof(int) * (size_t)t->n_index, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    cudaFree(t->hd.opt); cudaFree(t->hd.optcoef); t->hd.opt = nullptr; t->hd.optcoef = nullptr;
+    t->nOpt = n_opt;
+    if (n_opt > 0) {
+        if (!opt_obj) return fail(JSLP_E_INVALID, "opt_obj is NULL");
+        CK(cudaMalloc(&t->hd.opt, sizeof(double) * (size_t)n_opt * t->stride));
+        CK(cudaMalloc(&t->hd.optcoef, sizeof(double) * (size_t)n_opt));
+        CK(cudaMemsetAsync(t->hd.opt, 0, sizeof(double) * (size_t)n_opt * t->stride, s));
+        CK(cudaMemcpy2DAsync(t->hd.opt, sizeof(double) * t->stride, opt_obj, sizeof(double) * t->W,
+                             sizeof(double) * t->W, n_opt, cudaMemcpyHostToDevice, s));
+    }
+    t->feasible = 1; t->bounded = 1; t->simplexIters = 0; t->unboundedVar = -1;
+    t->evaluation = 0; t->bestPossibleEval = 0; t->isIntegralFlag = 0; t->bncIterations = 0;
+    t->nVars = t->W + t->H - 2;
+    t->lastElementIndex = t->nVars;
+    t->saved.valid = false;
+    int rc = push_desc(t);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    return JSLP_OK;
+}
+
+extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    switch (key) {
+        case JSLP_OPT_ENGINE:
+            if (value < 0 || value > 4) return fail(JSLP_E_INVALID, "engine must be 0..4");
+            t->engine = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_BATCH:
+            if (value < 1 || value > 4000) return fail(JSLP_E_INVALID, "batch must be 1..4000");
+            t->batch = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_PIVOT_LOG_CAP:
+            t->host_log_cap = (int64_t)value;
+            t->host_log.clear();
+            return JSLP_OK;
+    }
+    return fail(JSLP_E_INVALID, "unknown option");
+}
+
+// ---------------------------------------------------------------------------------------------
+static int step_grid(const jslp_tab *t) {
+    int g = t->ctx->num_sms * 2;
+    return std::max(1, std::min(g, t->rowcap));
+}
+
+static int build_graphs(jslp_tab *t) {
+    const int grid = step_grid(t);
+    const int smem = t->stride * 8;
+    if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem) return JSLP_OK;
+    drop_graphs(t);
+    cudaStream_t s = t->ctx->stream;
+    CK(cudaFuncSetAttribute(k_pivot_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int mode = 0; mode < 2; mode++) {
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
+        if (mode == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
+            k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
+            for (int i = 0; i < t->batch; i++) k_pivot_step<<<grid, STEP_THREADS, smem, s>>>(t->d_T, t->d_rec, 1);
+        } else {  // two kernels per pivot
+            for (int i = 0; i < t->batch; i++) {
+                k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
+                k_pivot_step<<<grid, STEP_THREADS, smem, s>>>(t->d_T, t->d_rec, 0);
+            }
+        }
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        cudaGraphExec_t ge;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+        if (mode == 0) t->g_fused = ge; else t->g_simple = ge;
+    }
+    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem;
+    return JSLP_OK;
+}
+
+static double js_round_h(double x) {
+    if (!(x == x) || std::isinf(x)) return x;
+    const double f = std::floor(x);
+    return (x - f >= 0.5) ? f + 1.0 : f;
+}
+
+// tableau.ts:420-430
+static void set_evaluation(jslp_tab *t, double raw) {
+    const double roundingCoeff = js_round_h(1 / t->precision);
+    const double rounded = js_round_h((2.220446049250313e-16 + raw) * roundingCoeff) / roundingCoeff;
+    t->evaluation = rounded;
+    if (t->simplexIters == 0) t->bestPossibleEval = rounded;
+}
+
+// checkForCycles (simplex.ts:415-440) under its calling discipline (called after every push,
+// stops at the first hit): a repeated block must end at the newest element, so only suffix
+// squares are examined; the literal scan reports the smallest start = the longest block.
+static bool cycle_hit(const std::vector<long long> &h, int *start, int *len) {
+    const long n = (long)h.size();
+    for (long L = n / 2; L >= 1; L--) {
+        const long e1 = n - 2 * L, e2 = n - L;
+        if (h[e1] != h[e2]) continue;
+        bool eq = true;
+        for (long i = 1; i < L; i++)
+            if (h[e1 + i] != h[e2 + i]) { eq = false; break; }
+        if (eq) { *start = (int)e1; *len = (int)L; return true; }
+    }
+    return false;
+}
+
+static int ensure_snapshot(jslp_tab *t) {
+    Snapshot &sn = t->snap;
+    if (sn.M && sn.rowcap == t->rowcap) return JSLP_OK;
+    free_snap(sn);
+    CK(cudaMalloc(&sn.M, sizeof(double) * (size_t)t->rowcap * t->stride));
+    CK(cudaMalloc(&sn.pcol, sizeof(double) * (size_t)t->rowcap));
+    CK(cudaMalloc(&sn.vrow, sizeof(int) * (size_t)t->rowcap));
+    CK(cudaMalloc(&sn.vcol, sizeof(int) * (size_t)t->W));
+    CK(cudaMalloc(&sn.prow, sizeof(double) * (size_t)t->stride));
+    CK(cudaMalloc(&sn.rec, sizeof(Rec)));
+    if (t->nOpt > 0) {
+        CK(cudaMalloc(&sn.opt, sizeof(double) * (size_t)t->nOpt * t->stride));
+        CK(cudaMalloc(&sn.optcoef, sizeof(double) * (size_t)t->nOpt));
+    }
+    sn.rowcap = t->rowcap;
+    return JSLP_OK;
+}
+
+static int snapshot_copy(jslp_tab *t, bool to_snapshot) {
+    Snapshot &sn = t->snap;
+    cudaStream_t s = t->ctx->stream;
+    auto cp = [&](void *live, void *snap, size_t bytes) {
+        return to_snapshot ? cudaMemcpyAsync(snap, live, bytes, cudaMemcpyDeviceToDevice, s)
+                           : cudaMemcpyAsync(live, snap, bytes, cudaMemcpyDeviceToDevice, s);
+    };
+    CK(cp(t->hd.M, sn.M, sizeof(double) * (size_t)t->H * t->stride));
+    CK(cp(t->hd.pcol, sn.pcol, sizeof(double) * (size_t)t->H));
+    CK(cp(t->hd.vrow, sn.vrow, sizeof(int) * (size_t)t->H));
+    CK(cp(t->hd.vcol, sn.vcol, sizeof(int) * (size_t)t->W));
+    CK(cp(t->hd.prow, sn.prow, sizeof(double) * (size_t)t->stride));
+    CK(cp(t->d_rec, sn.rec, sizeof(Rec)));
+    if (t->nOpt > 0) {
+        CK(cp(t->hd.opt, sn.opt, sizeof(double) * (size_t)t->nOpt * t->stride));
+        CK(cp(t->hd.optcoef, sn.optcoef, sizeof(double) * (size_t)t->nOpt));
+    }
+    return JSLP_OK;
+}
+
+static void fill_status(jslp_tab *t, jslp_lp_status *o, const Rec &r, int cycled, int cs, int cl, float ms,
+                        int64_t launches, int engine) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->feasible = t->feasible; o->bounded = t->bounded; o->cycled = cycled;
+    o->cycle_start = cs; o->cycle_length = cl;
+    o->phase1_pivots = r.p1; o->phase2_pivots = r.p2;
+    o->unbounded_var_index = t->unboundedVar; o->simplex_iters = t->simplexIters;
+    o->width = t->W; o->height = t->H; o->engine = engine;
+    o->evaluation_raw = r.eval_raw; o->evaluation = t->evaluation;
+    o->best_possible_eval = t->bestPossibleEval;
+    o->gpu_ms = ms; o->kernel_launches = launches;
+}
+
+// Runs phase1 and/or phase2 on the device.  only_phase: 0 = simplex(), 1 = phase1(), 2 = phase2().
+static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status *out, bool timed) {
+    jslp_ctx *ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int rc = build_graphs(t);
+    if (rc) return rc;
+    const int engine = (t->engine == 1) ? 1 : 2;
+    cudaGraphExec_t graph = engine == 1 ? t->g_simple : t->g_fused;
+    const int64_t launches_per_batch = engine == 1 ? 1 + 2 * (int64_t)t->batch : 2 + (int64_t)t->batch;
+    const int64_t launches0 = ctx->launches;
+
+    Rec init;
+    memset(&init, 0, sizeof(init));
+    init.status = ST_RUNNING;
+    init.phase = only_phase == 2 ? 2 : 1;
+    init.stop_at = -1;
+    init.unbounded_var = -1;
+    init.only_phase = only_phase;
+    *t->h_rec = init;
+    if (timed) CK(cudaEventRecord(ctx->ev0, s));
+    CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // h_rec is reused as the read-back buffer below
+
+    if (only_phase != 2) t->bounded = 1;  // simplex.ts:15
+    if (check_cycles) {
+        rc = ensure_snapshot(t);
+        if (rc) return rc;
+    }
+    std::vector<long long> hist1, hist2;  // (leaving, entering) per phase call
+    long selected = 0;                    // selections seen so far in this call
+    int cycled = 0, cyc_start = 0, cyc_len = 0;
+    Rec last = init;
+    for (;;) {
+        if (check_cycles) {
+            rc = snapshot_copy(t, true);
+            if (rc) return rc;
+        }
+        CK(cudaGraphLaunch(graph, s));
+        ctx->launches += launches_per_batch;
+        CK(cudaMemcpyAsync(t->h_rec, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(t->h_log, t->hd.plog, sizeof(int4) * (size_t)t->hd.plog_cap, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        last = *t->h_rec;
+        const int n_new = std::min(last.log_n, t->hd.plog_cap);
+        if (last.log_n > t->hd.plog_cap) return fail(JSLP_E_CAPACITY, "pivot log overflow inside one batch");
+        long hit_at = -1;
+        if (check_cycles) {
+            for (int i = 0; i < n_new; i++) {
+                const int4 e = t->h_log[i];
+                const int phase = (e.x >> 30) & 1 ? 2 : 1;
+                std::vector<long long> &h = phase == 1 ? hist1 : hist2;
+                h.push_back(((long long)e.z << 32) | (unsigned int)e.w);
+                if (cycle_hit(h, &cyc_start, &cyc_len)) { cycled = phase; hit_at = selected + i; break; }
+            }
+        }
+        if (hit_at >= 0) {
+            // The reference returns before executing the pivot that completes the repeat: replay
+            // this batch from its snapshot and stop after `hit_at` executed pivots.
+            rc = snapshot_copy(t, false);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(t->h_rec, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            Rec r = *t->h_rec;
+            // hit_at selections precede the offending one, so exactly hit_at pivots get executed;
+            // a pivot pending in the snapshot was selected in an earlier batch, hence done < hit_at.
+            r.stop_at = (int)hit_at;
+            *t->h_rec = r;
+            CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            CK(cudaGraphLaunch(graph, s));
+            ctx->launches += launches_per_batch;
+            CK(cudaMemcpyAsync(t->h_rec, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            last = *t->h_rec;
+            if (t->host_log_cap > 0)
+                for (long i = selected; i < hit_at && (int64_t)t->host_log.size() < t->host_log_cap; i++)
+                    t->host_log.push_back(t->h_log[i - selected]);
+            break;
+        }
+        if (t->host_log_cap > 0)
+            for (int i = 0; i < n_new && (int64_t)t->host_log.size() < t->host_log_cap; i++)
+                t->host_log.push_back(t->h_log[i]);
+        selected += n_new;
+        if (last.status != ST_RUNNING) break;
+    }
+    float ms = 0.f;
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev1, s));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    }
+
+    // Tableau flag contract (simplex.ts:51-54,73-76,90-91,265-269,298-303,317-318)
+    if (cycled) {
+        t->feasible = 0;
+    } else if (last.status == ST_INFEASIBLE) {
+        t->feasible = 0;
+    } else if (last.status == ST_P1_DONE) {
+        t->feasible = 1;
+    } else if (last.status == ST_OPTIMAL) {
+        if (only_phase != 2) t->feasible = 1;
+        set_evaluation(t, last.eval_raw);
+        t->simplexIters += 1;
+    } else if (last.status == ST_UNBOUNDED) {
+        if (only_phase != 2) t->feasible = 1;
+        t->evaluation = -INFINITY;
+        t->bounded = 0;
+        t->unboundedVar = last.unbounded_var;
+    }
+    fill_status(t, out, last, cycled, cyc_start, cyc_len, ms, ctx->launches - launches0, engine);
+    return JSLP_OK;
+}
+
+extern "C" int jslp_simplex(jslp_tab *t, int check_cycles, jslp_lp_status *out) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    return run_lp(t, 0, check_cycles, out, true);
+}
+extern "C" int jslp_phase1(jslp_tab *t, int check_cycles, jslp_lp_status *out) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    return run_lp(t, 1, check_cycles, out, true);
+}
+extern "C" int jslp_phase2(jslp_tab *t, int check_cycles, jslp_lp_status *out) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    return run_lp(t, 2, check_cycles, out, true);
+}
+
+extern "C" int jslp_pivot(jslp_tab *t, int row, int col) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    if (row < 0 || row >= t->H || col < 0 || col >= t->W) return fail(JSLP_E_INVALID, "pivot index out of range");
+    jslp_ctx *ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int smem = t->stride * 8;
+    CK(cudaFuncSetAttribute(k_pivot_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    Rec init;
+    memset(&init, 0, sizeof(init));
+    init.status = ST_RUNNING; init.phase = 2; init.stop_at = -1; init.unbounded_var = -1;
+    *t->h_rec = init;
+    CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
+    k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, row, col);
+    k_pivot_step<<<step_grid(t), STEP_THREADS, smem, s>>>(t->d_T, t->d_rec, 0);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return JSLP_OK;
+}
+
+// backup.ts:49-51 (copy): device snapshot
+extern "C" int jslp_save(jslp_tab *t) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    Saved &sv = t->saved;
+    if (!sv.M || sv.rowcap < t->H) {
+        free_saved(sv);
+        CK(cudaMalloc(&sv.M, sizeof(double) * (size_t)t->rowcap * t->stride));
+        CK(cudaMalloc(&sv.vrow, sizeof(int) * (size_t)t->rowcap));
+        CK(cudaMalloc(&sv.vcol, sizeof(int) * (size_t)t->W));
+        if (t->nOpt > 0) CK(cudaMalloc(&sv.opt, sizeof(double) * (size_t)t->nOpt * t->stride));
+        sv.rowcap = t->rowcap;
+    }
+    CK(cudaMemcpyAsync(sv.M, t->hd.M, sizeof(double) * (size_t)t->H * t->stride, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(sv.vrow, t->hd.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(sv.vcol, t->hd.vcol, sizeof(int) * (size_t)t->W, cudaMemcpyDeviceToDevice, s));
+    if (t->nOpt > 0)
+        CK(cudaMemcpyAsync(sv.opt, t->hd.opt, sizeof(double) * (size_t)t->nOpt * t->stride, cudaMemcpyDeviceToDevice, s));
+    sv.H = t->H; sv.nVars = t->nVars; sv.lastElementIndex = t->lastElementIndex;
+    sv.valid = true;
+    return JSLP_OK;
+}
+
+// backup.ts:53-105: feasible/bounded/evaluation are deliberately not restored
+extern "C" int jslp_restore(jslp_tab *t) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    Saved &sv = t->saved;
+    if (!sv.valid) return JSLP_OK;
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    CK(cudaMemcpyAsync(t->hd.M, sv.M, sizeof(double) * (size_t)sv.H * t->stride, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vrow, sv.vrow, sizeof(int) * (size_t)sv.H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vcol, sv.vcol, sizeof(int) * (size_t)t->W, cudaMemcpyDeviceToDevice, s));
+    if (t->nOpt > 0)
+        CK(cudaMemcpyAsync(t->hd.opt, sv.opt, sizeof(double) * (size_t)t->nOpt * t->stride, cudaMemcpyDeviceToDevice, s));
+    const bool changed = t->H != sv.H;
+    t->H = sv.H; t->nVars = sv.nVars; t->lastElementIndex = sv.lastElementIndex;
+    if (changed) return push_desc(t);
+    return JSLP_OK;
+}
+
+static int grow_rows(jslp_tab *t, int need) {
+    if (need <= t->rowcap) return JSLP_OK;
+    int cap = std::max(need, t->rowcap + t->rowcap / 2 + 8);
+    CK(cudaStreamSynchronize(t->ctx->stream));
+    int rc = alloc_rows(t, cap);
+    if (rc) return rc;
+    free_snap(t->snap);
+    return JSLP_OK;  // descriptor is pushed by the caller; graphs read pointers through it
+}
+
+extern "C" int jslp_add_cuts(jslp_tab *t, const jslp_cut *cuts, int n) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    if (n < 0 || (n > 0 && !cuts)) return fail(JSLP_E_INVALID, "bad cuts");
+    if (n == 0) {
+        t->nVars = t->W + t->H - 2;  // cutting-strategies.ts:33-34
+        return JSLP_OK;
+    }
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    const int grid_before = step_grid(t);
+    int rc = grow_rows(t, t->H + n);
+    if (rc) return rc;
+    if (n > t->cuts_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(t->d_cuts); cudaFreeHost(t->h_cuts);
+        t->cuts_cap = std::max(64, n * 2);
+        CK(cudaMalloc(&t->d_cuts, sizeof(CutDev) * (size_t)t->cuts_cap));
+        CK(cudaMallocHost(&t->h_cuts, sizeof(CutDev) * (size_t)t->cuts_cap));
+    } else {
+        CK(cudaStreamSynchronize(s));  // h_cuts may still be in flight from the previous call
+    }
+    for (int i = 0; i < n; i++) {
+        t->h_cuts[i].type = cuts[i].type;
+        t->h_cuts[i].var_index = cuts[i].var_index;
+        t->h_cuts[i].value = cuts[i].value;
+    }
+    CK(cudaMemcpyAsync(t->d_cuts, t->h_cuts, sizeof(CutDev) * (size_t)n, cudaMemcpyHostToDevice, s));
+    const int H0 = t->H;
+    t->H = H0 + n;
+    rc = push_desc(t);  // kernels below read pointers/sizes through the descriptor
+    if (rc) return rc;
+    k_add_cuts<<<n, 256, 0, s>>>(t->d_T, t->d_cuts, H0, t->lastElementIndex);
+    t->ctx->launches += 1;
+    CK(cudaGetLastError());
+    t->lastElementIndex += n;
+    t->nVars = t->W + t->H - 2 + n;  // cutting-strategies.ts:34,70 (the reference over-counts; kept)
+    if (step_grid(t) != grid_before) drop_graphs(t);
+    return JSLP_OK;
+}
+
+extern "C" int jslp_apply_cuts(jslp_tab *t, const jslp_cut *cuts, int n, int check_cycles, jslp_lp_status *out) {
+    int rc = jslp_restore(t);
+    if (rc) return rc;
+    rc = jslp_add_cuts(t, cuts, n);
+    if (rc) return rc;
+    return run_lp(t, 0, check_cycles, out, true);
+}
+
+static int mip_scan(jslp_tab *t, MipOut *o) {
+    if (t->n_int <= 0) { o->is_integral = 1; o->var_index = -1; o->value = 0; return JSLP_OK; }
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    k_mip_scan<<<1, 256, 0, s>>>(t->d_T, t->d_mip);
+    t->ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(t->h_mip, t->d_mip, sizeof(MipOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *o = *t->h_mip;
+    return JSLP_OK;
+}
+
+extern "C" int jslp_is_integral(jslp_tab *t, int *is_integral) {
+    if (!t || !is_integral) return fail(JSLP_E_INVALID, "NULL argument");
+    MipOut o;
+    int rc = mip_scan(t, &o);
+    if (rc) return rc;
+    *is_integral = o.is_integral;
+    return JSLP_OK;
+}
+extern "C" int jslp_most_fractional(jslp_tab *t, int32_t *var_index, double *value) {
+    if (!t || !var_index || !value) return fail(JSLP_E_INVALID, "NULL argument");
+    MipOut o;
+    int rc = mip_scan(t, &o);
+    if (rc) return rc;
+    *var_index = o.var_index;
+    *value = o.value;
+    return JSLP_OK;
+}
+
+extern "C" int jslp_download(jslp_tab *t, double *matrix, double *rhs_col, double *cost_row, int32_t *vrow,
+                             int32_t *vcol, double *opt_obj, int32_t *width, int32_t *height) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    if (width) *width = t->W;
+    if (height) *height = t->H;
+    if (matrix)
+        CK(cudaMemcpy2DAsync(matrix, sizeof(double) * t->W, t->hd.M, sizeof(double) * t->stride,
+                             sizeof(double) * t->W, t->H, cudaMemcpyDeviceToHost, s));
+    if (rhs_col)  // column 0 of every row: a strided D2H copy (8 bytes per row)
+        CK(cudaMemcpy2DAsync(rhs_col, sizeof(double), t->hd.M, sizeof(double) * t->stride, sizeof(double), t->H,
+                             cudaMemcpyDeviceToHost, s));
+    if (cost_row) CK(cudaMemcpyAsync(cost_row, t->hd.M, sizeof(double) * t->W, cudaMemcpyDeviceToHost, s));
+    if (vrow) CK(cudaMemcpyAsync(vrow, t->hd.vrow, sizeof(int) * t->H, cudaMemcpyDeviceToHost, s));
+    if (vcol) CK(cudaMemcpyAsync(vcol, t->hd.vcol, sizeof(int) * t->W, cudaMemcpyDeviceToHost, s));
+    if (opt_obj && t->nOpt > 0)
+        CK(cudaMemcpy2DAsync(opt_obj, sizeof(double) * t->W, t->hd.opt, sizeof(double) * t->stride,
+                             sizeof(double) * t->W, t->nOpt, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return JSLP_OK;
+}
+
+extern "C" int jslp_pivot_log(jslp_tab *t, int32_t *entries, int cap, int *n) {
+    if (!t || !n) return fail(JSLP_E_INVALID, "NULL argument");
+    const int m = (int)std::min<int64_t>((int64_t)t->host_log.size(), cap);
+    for (int i = 0; i < m && entries; i++) {
+        entries[4 * i + 0] = t->host_log[i].x & 0x3fffffff;
+        entries[4 * i + 1] = t->host_log[i].y;
+        entries[4 * i + 2] = t->host_log[i].z;
+        entries[4 * i + 3] = t->host_log[i].w;
+    }
+    *n = (int)t->host_log.size();
+    t->host_log.clear();
+    return JSLP_OK;
+}
+
+#include "jslp_bnb.cuh"

@@ -1,0 +1,660 @@
+// jslpsolver_b200/csrc/jslp_kernels.cuh -- sm_100a kernels for the dense-tableau pivot path.
+//
+// What the reference does per simplex iteration (src/tableau/simplex.ts in JWally/jsLPSolver):
+//   phase1 (25-98)   leaving row = arg-min RHS < -precision, entering column = arg-max -cost/coef
+//   phase2 (100-325) entering column = arg-max reduced cost > precision inside the first 50-column
+//                    batch that has one (partial pricing), ratio test with degenerate early exit
+//   pivot  (330-413) normalise pivot row, rank-1 update of every other row incl. the cost row
+// All of it is "strict compare, lowest index wins" on IEEE fp64 with separate multiply and
+// subtract roundings (JS has no FMA), so every reduction here is on (value,index) pairs and the
+// update uses __dmul_rn/__dsub_rn.
+//
+// Kernels:
+//   k_select      one CTA decides the next pivot from the tableau in HBM/L2 and stages the raw
+//                 pivot row / pivot column into side buffers (also used for Tableau.pivot()).
+//   k_pivot_step  multi-CTA fused step: TMA-stages the raw pivot row into shared memory,
+//                 normalises it there, streams its row block with 128-bit loads/stores doing the
+//                 rank-1 update; the last CTA to finish (atomic ticket) runs the selection for the
+//                 NEXT pivot, so one launch == one simplex iteration and a CUDA graph of N launches
+//                 needs no host round trip.  Memory-bound (0.125 flop/B): no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+#include <math.h>
+
+namespace jslp {
+
+enum { ST_RUNNING = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_P1_DONE = 4 };
+
+// Device-resident description of one tableau (kernels read it through a pointer so that a
+// captured CUDA graph stays valid when H grows or buffers are re-allocated).
+struct TabDev {
+    double *M;             // rowcap x stride, row-major; row 0 = cost row, col 0 = RHS
+    int *vrow;             // varIndexByRow [rowcap]
+    int *vcol;             // varIndexByCol [W]
+    unsigned char *unres;  // unrestrictedVars by var index [n_index] or nullptr
+    double *opt;           // optional objective reducedCosts [nOpt x stride]
+    double *prow;          // staged raw pivot row [stride]
+    double *pcol;          // staged raw pivot column [rowcap]
+    double *optcoef;       // staged optional-objective pivot-column entries [nOpt]
+    int4 *plog;            // per-batch pivot log (row, col, leaving var, entering var)
+    unsigned char *optflag; // scratch [W] for the optional-objective tie-break lists
+    int *intpos;           // position in model.integerVariables by var index, -1 otherwise [n_index]
+    int W, H, stride, rowcap;
+    int nOpt, n_index, plog_cap;
+    int batch_size, use_partial;  // phase-2 partial pricing (simplex.ts:118-127)
+    double prec;
+};
+
+// Pivot record: the decision carried from one launch to the next.
+struct Rec {
+    int status;      // ST_*
+    int phase;       // 1 or 2
+    int has_pivot;   // (r, c) is selected and staged but not executed yet
+    int r, c;
+    int is_neg;      // isReducedCostNegative (simplex.ts:138)
+    int flush;       // some row other than r has a non-zero pivot-column entry (simplex.ts:380)
+    int done;        // pivots executed in this call
+    int p1, p2;      // per-phase pivot counts (return values of phase1()/phase2())
+    int stop_at;     // execute at most this many pivots (-1 = no limit); used for cycle rewind
+    int log_n;       // entries in plog for the current batch
+    int unbounded_var;
+    int only_phase;  // 0 = simplex(), 1 = phase1() only, 2 = phase2() only
+    unsigned int ticket;
+    int pad;
+    double q;        // raw pivot element
+    double eval_raw; // matrix[0] at exit
+};
+
+struct MipOut {
+    int is_integral;
+    int var_index;
+    double value;
+};
+
+__device__ __forceinline__ bool nz16(double v) { return !(v >= -1e-16 && v <= 1e-16); }
+
+__device__ __forceinline__ double ldg_cg(const double *p) { return __ldcg(p); }
+
+// JS Math.round: nearest, ties toward +inf
+__device__ __forceinline__ double js_round(double x) {
+    if (!(x == x) || isinf(x)) return x;
+    const double f = floor(x);
+    return (x - f >= 0.5) ? f + 1.0 : f;
+}
+
+struct VI {
+    double v;
+    int i;
+};
+
+template <bool IS_MIN>
+__device__ __forceinline__ bool better(const VI &b, const VI &a) {
+    if (IS_MIN) return b.v < a.v || (b.v == a.v && b.i < a.i);
+    return b.v > a.v || (b.v == a.v && b.i < a.i);
+}
+
+struct RedSmem {
+    double v[32];
+    int i[32];
+};
+
+// (value,index) arg-min / arg-max over the CTA, lowest index wins ties; result on every thread.
+template <bool IS_MIN>
+__device__ VI block_reduce_vi(VI x, const VI init, RedSmem &s) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        VI y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+        if (better<IS_MIN>(y, x)) x = y;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) { s.v[w] = x.v; s.i[w] = x.i; }
+    __syncthreads();
+    if (l < nw) { x.v = s.v[l]; x.i = s.i[l]; } else { x = init; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        VI y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+        if (better<IS_MIN>(y, x)) x = y;
+    }
+    return x;
+}
+
+// op: 0 = min, 1 = sum
+template <int OP>
+__device__ int block_reduce_int(int x, RedSmem &s) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int y = __shfl_xor_sync(0xffffffffu, x, o);
+        x = OP == 0 ? min(x, y) : x + y;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) s.i[w] = x;
+    __syncthreads();
+    x = (l < nw) ? s.i[l] : (OP == 0 ? INT_MAX : 0);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int y = __shfl_xor_sync(0xffffffffu, x, o);
+        x = OP == 0 ? min(x, y) : x + y;
+    }
+    return x;
+}
+
+__device__ __forceinline__ bool is_unres(const TabDev &T, int varIndex) {
+    return T.unres != nullptr && varIndex >= 0 && varIndex < T.n_index && T.unres[varIndex] != 0;
+}
+
+// Literal, single-thread restatement of the pricing loop with optional objectives
+// (simplex.ts:132-263).  Only models with constraint weight/priority have them (tiny fixtures),
+// so the rare path trades speed for an exact transcription of the list semantics.
+__device__ void price_with_optional_seq(const TabDev &T, int *outCol, int *outNeg) {
+    const double prec = T.prec;
+    const double *cost = T.M;
+    const int lastColumn = T.W - 1;
+    int enteringColumn = 0, isNeg = 0;
+    double enteringValue = prec;
+    unsigned char *flag = T.optflag;  // 1 = column is on the tie-break list
+    for (int c = 0; c < T.W; c++) flag[c] = 0;
+    int listed = 0;
+    auto price = [&](int c, double rc) {
+        if (is_unres(T, T.vcol[c]) && rc < 0) {
+            if (-rc > enteringValue) { enteringValue = -rc; enteringColumn = c; isNeg = 1; }
+            return;
+        }
+        if (rc > enteringValue) { enteringValue = rc; enteringColumn = c; isNeg = 0; }
+    };
+    if (T.use_partial) {
+        const int nColumns = lastColumn;
+        const int totalBatches = (nColumns + T.batch_size - 1) / T.batch_size;
+        int batchStart = 1, scanned = 0;
+        while (enteringColumn == 0 && scanned < totalBatches) {
+            int batchEnd = batchStart + T.batch_size - 1;
+            if (batchEnd > lastColumn) batchEnd = lastColumn;
+            for (int c = batchStart; c <= batchEnd; c++) {
+                const double rc = ldg_cg(cost + c);
+                if (-prec < rc && rc < prec) { flag[c] = 1; listed++; continue; }
+                price(c, rc);
+            }
+            batchStart = batchEnd >= lastColumn ? 1 : batchEnd + 1;
+            scanned++;
+        }
+    } else {
+        for (int c = 1; c <= lastColumn; c++) {
+            const double rc = ldg_cg(cost + c);
+            if (-prec < rc && rc < prec) { flag[c] = 1; listed++; continue; }
+            price(c, rc);
+        }
+    }
+    int o = 0;
+    while (enteringColumn == 0 && listed > 0 && o < T.nOpt) {
+        const double *rcs = T.opt + (size_t)o * T.stride;
+        enteringValue = prec;
+        int kept = 0;
+        for (int c = 1; c <= lastColumn; c++) {
+            if (!flag[c]) continue;
+            const double rc = ldg_cg(rcs + c);
+            if (-prec < rc && rc < prec) { kept++; continue; }
+            flag[c] = 0;
+            price(c, rc);
+        }
+        listed = kept;
+        o++;
+    }
+    *outCol = enteringColumn;
+    *outNeg = isNeg;
+}
+
+struct SelSmem {
+    RedSmem red;
+    int bc_col, bc_neg;
+};
+
+// Stage pivot (rstar, cstar): raw pivot row -> prow, optional pivot-column entries, label swap,
+// pivot log, record.  `cnt` = number of rows r (incl. row 0 and rstar) with a non-zero
+// pivot-column entry; pcol must already be staged.
+__device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar, int cstar,
+                                int isneg, int cnt) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const double *prowsrc = T.M + (size_t)rstar * T.stride;
+    for (int c = tid; c < T.stride; c += NT) T.prow[c] = c < T.W ? ldg_cg(prowsrc + c) : 0.0;
+    for (int o = tid; o < T.nOpt; o += NT) T.optcoef[o] = ldg_cg(T.opt + (size_t)o * T.stride + cstar);
+    if (tid == 0) {
+        const double q = ldg_cg(prowsrc + cstar);
+        const int leaving = T.vrow[rstar], entering = T.vcol[cstar];
+        if (rec->log_n < T.plog_cap) T.plog[rec->log_n] = make_int4(rstar | (phase == 2 ? (1 << 30) : 0), cstar, leaving, entering);
+        rec->log_n += 1;
+        T.vrow[rstar] = entering;  // simplex.ts:339-349 (the inverse maps are rebuilt on read-back)
+        T.vcol[cstar] = leaving;
+        rec->phase = phase;
+        rec->r = rstar;
+        rec->c = cstar;
+        rec->q = q;
+        rec->is_neg = isneg;
+        rec->flush = (cnt - (nz16(q) ? 1 : 0)) > 0;
+        rec->has_pivot = 1;
+    }
+}
+
+// One CTA decides the next pivot from the tableau as it stands in L2/HBM (phase1: simplex.ts:
+// 38-76, phase2: 129-303) and stages it.  All tableau reads bypass L1 (__ldcg): in the fused
+// kernel this runs after other CTAs have just rewritten the tableau.
+__device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int W = T.W, H = T.H;
+    const size_t stride = (size_t)T.stride;
+    const double prec = T.prec;
+    const double *M = T.M;
+    int phase = rec->phase;
+    const int only_phase = rec->only_phase;
+    int rstar = -1, cstar = -1, isneg = 0, cnt = 0;
+    bool col_staged = false;
+
+    if (phase == 1) {
+        const VI init = {-prec, INT_MAX};
+        VI b = init;
+        for (int r = 1 + tid; r < H; r += NT) {
+            const double v = ldg_cg(M + r * stride);
+            if (v < b.v) { b.v = v; b.i = r; }
+        }
+        b = block_reduce_vi<true>(b, init, s.red);
+        if (b.i == INT_MAX) {  // feasible (simplex.ts:51-54)
+            if (only_phase == 1) {
+                if (tid == 0) { rec->status = ST_P1_DONE; rec->has_pivot = 0; rec->eval_raw = ldg_cg(M); }
+                return;
+            }
+            phase = 2;
+        } else {
+            rstar = b.i;
+            const VI einit = {-INFINITY, INT_MAX};
+            VI e = einit;
+            const double *lrow = M + rstar * stride;
+            for (int c = 1 + tid; c < W; c += NT) {
+                const double coef = ldg_cg(lrow + c);
+                if (is_unres(T, T.vcol[c]) || coef < -prec) {
+                    const double quo = -ldg_cg(M + c) / coef;
+                    if (e.v < quo) { e.v = quo; e.i = c; }
+                }
+            }
+            e = block_reduce_vi<false>(e, einit, s.red);
+            if (e.i == INT_MAX) {  // simplex.ts:73-76
+                if (tid == 0) { rec->status = ST_INFEASIBLE; rec->has_pivot = 0; rec->eval_raw = ldg_cg(M); }
+                return;
+            }
+            cstar = e.i;
+        }
+    }
+
+    if (rstar < 0) {  // phase 2
+        if (T.nOpt == 0) {
+            const int nColumns = W - 1;
+            const int bsz = T.use_partial ? T.batch_size : nColumns;
+            const int nb = T.use_partial ? (nColumns + bsz - 1) / bsz : 1;
+            const VI init = {prec, INT_MAX};
+            for (int b = 0; b < nb && cstar < 0; b++) {
+                const int start = 1 + b * bsz;
+                const int end = min(start + bsz - 1, W - 1);
+                VI x = init;
+                for (int c = start + tid; c <= end; c += NT) {
+                    const double rc = ldg_cg(M + c);
+                    const double v = (rc < 0 && is_unres(T, T.vcol[c])) ? -rc : rc;
+                    if (v > x.v) { x.v = v; x.i = c; }
+                }
+                x = block_reduce_vi<false>(x, init, s.red);
+                if (x.i != INT_MAX) cstar = x.i;
+            }
+            if (cstar >= 0) isneg = (ldg_cg(M + cstar) < 0 && is_unres(T, T.vcol[cstar])) ? 1 : 0;
+        } else {
+            if (tid == 0) {
+                int c0, n0;
+                price_with_optional_seq(T, &c0, &n0);
+                s.bc_col = c0;
+                s.bc_neg = n0;
+            }
+            __syncthreads();
+            cstar = s.bc_col > 0 ? s.bc_col : -1;
+            isneg = s.bc_neg;
+            __syncthreads();
+        }
+        if (cstar < 0) {  // optimal (simplex.ts:265-269); setEvaluation rounding is done on the host
+            if (tid == 0) { rec->status = ST_OPTIMAL; rec->phase = 2; rec->has_pivot = 0; rec->eval_raw = ldg_cg(M); }
+            return;
+        }
+        // ratio test (simplex.ts:271-296) fused with staging of the pivot column
+        const VI init = {INFINITY, INT_MAX};
+        VI m = init;
+        int dmin = INT_MAX;
+        for (int r = tid; r < H; r += NT) {
+            const double col = ldg_cg(M + r * stride + cstar);
+            T.pcol[r] = col;
+            if (nz16(col)) cnt++;
+            if (r == 0) continue;
+            if (-prec < col && col < prec) continue;
+            const double rhs = ldg_cg(M + r * stride);
+            if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
+            const double quo = isneg ? -rhs / col : rhs / col;
+            if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+        }
+        dmin = block_reduce_int<0>(dmin, s.red);
+        m = block_reduce_vi<true>(m, init, s.red);
+        cnt = block_reduce_int<1>(cnt, s.red);
+        col_staged = true;
+        if (dmin != INT_MAX) rstar = dmin;
+        else if (m.i != INT_MAX) rstar = m.i;
+        else {  // unbounded (simplex.ts:298-303)
+            if (tid == 0) {
+                rec->status = ST_UNBOUNDED; rec->phase = 2; rec->has_pivot = 0;
+                rec->unbounded_var = T.vcol[cstar];
+                rec->eval_raw = ldg_cg(M);
+            }
+            return;
+        }
+    }
+
+    if (!col_staged) {
+        cnt = 0;
+        for (int r = tid; r < H; r += NT) {
+            const double col = ldg_cg(M + r * stride + cstar);
+            T.pcol[r] = col;
+            if (nz16(col)) cnt++;
+        }
+        cnt = block_reduce_int<1>(cnt, s.red);
+    }
+    cta_stage_pivot(T, rec, phase, rstar, cstar, isneg, cnt);
+}
+
+// Standalone selection (engine 1, the first pivot of every solve, and Tableau.pivot()).
+// force_r/force_c >= 0: stage exactly that pivot (== Tableau.pivot(r, c)).
+__global__ void __launch_bounds__(512) k_select(const TabDev *Tp, Rec *rec, int force_r, int force_c) {
+    __shared__ SelSmem s;
+    __shared__ TabDev T;
+    if (threadIdx.x == 0) T = *Tp;
+    __syncthreads();
+    if (force_r >= 0) {
+        int cnt = 0;
+        for (int r = threadIdx.x; r < T.H; r += blockDim.x) {
+            const double col = ldg_cg(T.M + (size_t)r * T.stride + force_c);
+            T.pcol[r] = col;
+            if (nz16(col)) cnt++;
+        }
+        cnt = block_reduce_int<1>(cnt, s.red);
+        cta_stage_pivot(T, rec, rec->phase, force_r, force_c, 0, cnt);
+        return;
+    }
+    if (rec->status != ST_RUNNING || rec->has_pivot) return;
+    if (rec->stop_at >= 0 && rec->done >= rec->stop_at) return;
+    cta_select(T, rec, s);
+}
+
+// ---- TMA (1-D bulk copy) + mbarrier helpers: raw pivot row HBM/L2 -> shared memory ----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ double2 ld_v2(const double *p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_v2(double *p, double2 v) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+constexpr int STEP_THREADS = 256;
+constexpr int ROW_CHUNK = 8;
+
+// Shared-memory staging + normalisation of the pivot row (simplex.ts:352-364 and the lazy flush
+// of 380-382): frow[c] = final content of the pivot row after the pivot.
+__device__ __forceinline__ void stage_pivot_row(const TabDev &T, double *frow, uint64_t *bar, uint32_t parity,
+                                                int cstar, double q, int flush) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t bytes = (uint32_t)T.stride * 8u;
+    if (tid == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(frow, T.prow, bytes, bar);
+    }
+    mbar_wait(bar, parity);
+    for (int c = tid; c < T.stride; c += NT) {
+        const double v = frow[c];
+        double f = nz16(v) ? v / q : 0.0;
+        if (c == cstar) f = 1.0 / q;
+        if (flush && !nz16(f) && f != 0.0) f = 0.0;
+        frow[c] = f;
+    }
+    __syncthreads();
+}
+
+// Rank-1 update of rows [r0, r0+nr) (simplex.ts:367-391), pivot row rewrite, optional rows.
+__device__ __forceinline__ void update_rows(const TabDev &T, const double *frow, int r0, int nr, int rstar,
+                                            int cstar, double q, bool do_opt) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const size_t stride = (size_t)T.stride;
+    const int npair = T.stride >> 1;
+    const double2 *frow2 = reinterpret_cast<const double2 *>(frow);
+    const int cpair = cstar >> 1;
+    for (int rb = r0; rb < r0 + nr; rb += ROW_CHUNK) {
+        double coef[ROW_CHUNK];
+        bool act[ROW_CHUNK];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < ROW_CHUNK; j++) {
+            const int r = rb + j;
+            const bool valid = (r < r0 + nr) && (r != rstar);
+            coef[j] = valid ? T.pcol[r] : 0.0;
+            act[j] = valid && nz16(coef[j]);
+            any |= act[j];
+            if (valid && !act[j] && coef[j] != 0.0 && tid == 0) T.M[r * stride + cstar] = 0.0;  // simplex.ts:386-388
+        }
+        if (any) {
+            for (int c2 = tid; c2 < npair; c2 += NT) {
+                const double2 f = frow2[c2];
+                const bool z0 = nz16(f.x), z1 = nz16(f.y);
+                const bool pc = (c2 == cpair);
+                if (!z0 && !z1 && !pc) continue;  // zero pivot-row entries touch nothing (nonZeroColumns)
+                double2 old[ROW_CHUNK];
+#pragma unroll
+                for (int j = 0; j < ROW_CHUNK; j++)
+                    if (act[j]) old[j] = ld_v2(T.M + (rb + j) * stride + 2 * c2);
+#pragma unroll
+                for (int j = 0; j < ROW_CHUNK; j++) {
+                    if (!act[j]) continue;
+                    double2 nv = old[j];
+                    if (z0) nv.x = __dsub_rn(old[j].x, __dmul_rn(coef[j], f.x));
+                    if (z1) nv.y = __dsub_rn(old[j].y, __dmul_rn(coef[j], f.y));
+                    if (pc) {
+                        const double pv = -coef[j] / q;  // simplex.ts:385
+                        if (cstar & 1) nv.y = pv; else nv.x = pv;
+                    }
+                    st_v2(T.M + (rb + j) * stride + 2 * c2, nv);
+                }
+            }
+        }
+        if (rstar >= rb && rstar < rb + ROW_CHUNK && rstar < r0 + nr) {
+            double *dst = T.M + rstar * stride;
+            for (int c = tid; c < T.stride; c += NT) dst[c] = frow[c];
+        }
+    }
+    if (do_opt) {  // simplex.ts:393-412 (exact-zero predicates)
+        for (int o = 0; o < T.nOpt; o++) {
+            const double coefficient = T.optcoef[o];
+            if (coefficient == 0.0) continue;
+            double *rc = T.opt + (size_t)o * stride;
+            for (int c = tid; c < T.W; c += NT) {
+                const double v0 = frow[c];
+                double v = rc[c];
+                bool wr = false;
+                if (v0 != 0.0) { v = __dsub_rn(v, __dmul_rn(coefficient, v0)); wr = true; }
+                if (c == cstar) { v = -coefficient / q; wr = true; }
+                if (wr) rc[c] = v;
+            }
+        }
+    }
+}
+
+// One launch == one simplex iteration.  do_select: the last CTA selects the next pivot.
+__global__ void __launch_bounds__(STEP_THREADS, 2) k_pivot_step(const TabDev *Tp, Rec *rec, int do_select) {
+    extern __shared__ __align__(128) double frow[];
+    __shared__ TabDev T;
+    __shared__ SelSmem sel;
+    __shared__ uint64_t bar;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    if (rec->status != ST_RUNNING || !rec->has_pivot) return;
+    if (rec->stop_at >= 0 && rec->done >= rec->stop_at) return;
+    if (tid == 0) {
+        T = *Tp;
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int rstar = rec->r, cstar = rec->c, flush = rec->flush;
+    const double q = rec->q;
+    stage_pivot_row(T, frow, &bar, 0, cstar, q, flush);
+
+    const int G = gridDim.x, b = blockIdx.x;
+    const int base = T.H / G, rem = T.H % G;
+    const int r0 = b * base + min(b, rem);
+    const int nr = base + (b < rem ? 1 : 0);
+    update_rows(T, frow, r0, nr, rstar, cstar, q, b == G - 1);
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(&rec->ticket, 1u);
+        s_last = (t == (unsigned int)(G - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        rec->ticket = 0;
+        rec->done += 1;
+        if (rec->phase == 1) rec->p1 += 1; else rec->p2 += 1;
+        rec->has_pivot = 0;
+    }
+    __syncthreads();
+    if (do_select && !(rec->stop_at >= 0 && rec->done >= rec->stop_at)) cta_select(T, rec, sel);
+}
+
+// Start of every enqueued batch: empty the per-batch pivot log.
+__global__ void k_batch_begin(Rec *rec) {
+    if (threadIdx.x == 0) rec->log_n = 0;
+}
+
+// addCutConstraints (cutting-strategies.ts:36-71): one CTA per cut row, expressed in the
+// current basis.  Cut h becomes row H0 + h with slack index first_index + h.
+struct CutDev {
+    int type, var_index;
+    double value;
+};
+__global__ void __launch_bounds__(256) k_add_cuts(const TabDev *Tp, const CutDev *cuts, int H0, int first_index) {
+    __shared__ int s_row, s_col;
+    const TabDev &T = *Tp;
+    const int h = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const CutDev cut = cuts[h];
+    if (tid == 0) { s_row = -1; s_col = -1; }
+    __syncthreads();
+    for (int r = 1 + tid; r < H0; r += NT) if (T.vrow[r] == cut.var_index) s_row = r;
+    for (int c = 1 + tid; c < T.W; c += NT) if (T.vcol[c] == cut.var_index) s_col = c;
+    __syncthreads();
+    const double sign = cut.type == 0 ? -1.0 : 1.0;
+    double *crow = T.M + (size_t)(H0 + h) * T.stride;
+    if (s_row < 0) {
+        for (int c = tid; c < T.stride; c += NT) {
+            double v = 0.0;
+            if (c == 0) v = sign * cut.value;
+            else if (c == s_col) v = sign;
+            crow[c] = v;
+        }
+    } else {
+        const double *vr = T.M + (size_t)s_row * T.stride;
+        for (int c = tid; c < T.stride; c += NT) {
+            double v = 0.0;
+            if (c == 0) v = sign * (cut.value - vr[0]);
+            else if (c < T.W) v = -sign * vr[c];
+            crow[c] = v;
+        }
+    }
+    if (tid == 0) T.vrow[H0 + h] = first_index + h;
+}
+
+// isIntegral + getMostFractionalVar (mip-utils.ts:43-61,100-126) over the RHS column.
+__global__ void __launch_bounds__(256) k_mip_scan(const TabDev *Tp, MipOut *out) {
+    __shared__ RedSmem red;
+    const TabDev &T = *Tp;
+    const VI init = {0.0, INT_MAX};
+    VI best = init;  // (fraction, position in model.integerVariables)
+    int nonint = 0;
+    for (int r = 1 + threadIdx.x; r < T.H; r += blockDim.x) {
+        const int v = T.vrow[r];
+        if (v < 0 || v >= T.n_index) continue;
+        const int p = T.intpos[v];
+        if (p < 0) continue;
+        const double x = T.M[(size_t)r * T.stride];
+        const double fr = fabs(x - js_round(x));
+        if (fr > T.prec) nonint = 1;
+        if (fr > best.v || (fr == best.v && fr > 0.0 && p < best.i)) { best.v = fr; best.i = p; }
+    }
+    best = block_reduce_vi<false>(best, init, red);
+    nonint = block_reduce_int<1>(nonint, red);
+    if (threadIdx.x == 0) { out->is_integral = nonint == 0; out->var_index = -1; out->value = 0.0; }
+    __syncthreads();
+    if (best.i != INT_MAX && best.v > 0.0) {
+        for (int r = 1 + threadIdx.x; r < T.H; r += blockDim.x) {
+            const int v = T.vrow[r];
+            if (v >= 0 && v < T.n_index && T.intpos[v] == best.i) {
+                out->var_index = v;
+                out->value = T.M[(size_t)r * T.stride];
+            }
+        }
+    }
+}
+
+// Layout conversion between the reference's stride == width matrix and the padded device rows.
+__global__ void k_pack_rows(double *dst, int dstride, const double *src, int sstride, int rows, int cols,
+                            int zero_pad) {
+    const int r = blockIdx.y;
+    if (r >= rows) return;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (zero_pad ? dstride : cols); c += gridDim.x * blockDim.x)
+        dst[(size_t)r * dstride + c] = c < cols ? src[(size_t)r * sstride + c] : 0.0;
+}
+__global__ void k_gather_col(double *dst, const double *M, int stride, int rows, int col) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
+        dst[r] = M[(size_t)r * stride + col];
+}
+
+}  // namespace jslp

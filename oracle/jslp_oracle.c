@@ -96,6 +96,8 @@ typedef struct orc_tab {
     orc_cut *bestCuts;
     int nBestCuts;
     int *nzc; /* pivot scratch: nonZeroColumns (simplex.ts:328) */
+    long pivotLimit; /* bench sampling only: stop a phase loop after this many pivots (0 = off) */
+    int truncated;
 } orc_tab;
 
 /* JS Math.round: nearest integer, ties toward +Infinity */
@@ -366,6 +368,7 @@ long orc_phase1(orc_tab *t) {
             pl_push(&pl, t->vrow[leavingRow], t->vcol[enteringColumn]);
             if (check_cycle(t, &pl, 1)) { t->feasible = 0; break; }
         }
+        if (t->pivotLimit > 0 && t->totalPivots >= t->pivotLimit) { t->truncated = 1; t->feasible = 0; break; }
         orc_pivot(t, leavingRow, enteringColumn);
         iterations++;
     }
@@ -495,6 +498,7 @@ long orc_phase2(orc_tab *t) {
             pl_push(&pl, t->vrow[leavingRow], t->vcol[enteringColumn]);
             if (check_cycle(t, &pl, 2)) { t->feasible = 0; break; }
         }
+        if (t->pivotLimit > 0 && t->totalPivots >= t->pivotLimit) { t->truncated = 1; break; }
         orc_pivot(t, leavingRow, enteringColumn);
         iterations++;
     }
@@ -816,4 +820,6 @@ void orc_get_optional(const orc_tab *t, double *out) {
 void orc_get_pivot_log(const orc_tab *t, int *out) { memcpy(out, t->plog, sizeof(int) * 4 * (size_t)t->plogN); }
 void orc_get_node_log(const orc_tab *t, double *out) { memcpy(out, t->nlog, sizeof(double) * 8 * (size_t)t->nlogN); }
 void orc_get_best_cuts(const orc_tab *t, orc_cut *out) { memcpy(out, t->bestCuts, sizeof(orc_cut) * t->nBestCuts); }
+void orc_set_pivot_limit(orc_tab *t, long limit) { t->pivotLimit = limit; t->truncated = 0; }
+int orc_truncated(const orc_tab *t) { return t->truncated; }
 void orc_set_flags(orc_tab *t, int feasible, int bounded) { t->feasible = feasible; t->bounded = bounded; }

@@ -91,6 +91,9 @@ def lib():
         L.orc_row_of.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_row_of.restype = ctypes.c_int
         L.orc_set_flags.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.orc_set_pivot_limit.argtypes = [ctypes.c_void_p, ctypes.c_long]
+        L.orc_truncated.argtypes = [ctypes.c_void_p]
+        L.orc_truncated.restype = ctypes.c_int
         L.orc_cycles_ref.argtypes = [ctypes.c_void_p, ctypes.c_long,
                                      ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_long)]
         L.orc_cycles_fast.argtypes = L.orc_cycles_ref.argtypes
@@ -567,6 +570,12 @@ class OracleTableau:
         if getattr(self, "h", None):
             lib().orc_destroy(self.h)
             self.h = None
+
+    def set_pivot_limit(self, n):
+        lib().orc_set_pivot_limit(self.h, int(n))
+
+    def truncated(self):
+        return bool(lib().orc_truncated(self.h))
 
     def simplex(self):
         lib().orc_simplex(self.h)

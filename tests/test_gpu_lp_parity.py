@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+Bit-exact for everything integer (flags, pivot sequence, basis index arrays) AND for the fp64
+tableau itself: both sides perform the same IEEE operations in the same order per element, so
+the whole matrix must be identical, not merely close (the north_star's 1e-9 is the outer bar)."""
+import numpy as np
+import pytest
+
+from conftest import load_bundle
+from helpers import compare_solutions, strip_timeouts
+
+pytestmark = pytest.mark.gpu
+BUNDLE = load_bundle()
+ASSIGNMENT_UNCONFIRMED = {"StockCuttingProblem.json", "Vendor Selection.json"}
+ENGINES = {"two_kernel": 1, "fused": 2}
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return False
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def oracle_lp(it, precision=1e-8, check_cycles=True, log=1 << 16):
+    from oracle import ref_model
+    t = ref_model.OracleTableau(it.matrix, it.varIndexByRow, it.varIndexByCol, precision=precision,
+                                unrestricted=it.unrestricted, integers=it.integerIndices,
+                                opt_rc=it.optionalCosts, check_cycles=check_cycles, fast_cycles=True,
+                                pivot_log=log)
+    return t
+
+
+def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
+    from jslpsolver_b200 import _lib
+    from jslpsolver_b200.tableau import GpuTableau
+    g = GpuTableau(precision)
+    g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, it.unrestricted, it.integerIndices, it.optionalCosts)
+    g.set_option(_lib.OPT_ENGINE, engine)
+    g.set_option(_lib.OPT_PIVOT_LOG_CAP, log)
+    if batch:
+        g.set_option(_lib.OPT_BATCH, batch)
+    return g
+
+
+def assert_lp_parity(g, o, what=""):
+    st, os_ = g.lastStatus, o.state()
+    glog, olog = g.pivot_log(), o.pivot_log()
+    n = min(len(glog), len(olog))
+    if not np.array_equal(glog[:n], olog[:n]) or len(glog) != len(olog):
+        first = next((i for i in range(n) if not np.array_equal(glog[i], olog[i])), n)
+        raise AssertionError(f"{what}: pivot sequence differs at pivot {first}: gpu={glog[first:first+3].tolist()} "
+                             f"oracle={olog[first:first+3].tolist()} (lengths {len(glog)} vs {len(olog)})")
+    assert (bool(st.feasible), bool(st.bounded)) == (bool(os_.feasible), bool(os_.bounded)), what
+    assert (st.phase1_pivots, st.phase2_pivots) == (os_.lastP1, os_.lastP2), what
+    assert st.cycled == os_.cyclePhase, what
+    if st.cycled:
+        assert (st.cycle_start, st.cycle_length) == (os_.cycleStart, os_.cycleLen), what
+    vr, vc = o.maps()
+    assert np.array_equal(g.varIndexByRow, vr) and np.array_equal(g.varIndexByCol, vc), what
+    assert same_bits(g.matrix2d(), o.matrix()), f"{what}: tableau bits differ"
+    if st.feasible and st.bounded and not st.cycled:
+        assert same_bits(st.evaluation, os_.evaluation), what
+    if g.nOpt:
+        assert same_bits(g.optional_reduced_costs(), o.optional()), what
+
+
+# ------------------------------------------------------------------ golden fixtures end to end
+@pytest.mark.parametrize("fx", BUNDLE["fixtures"] + BUNDLE["readme"], ids=lambda f: f["file"])
+def test_fixture_solve_matches_reference_expects_and_oracle(fx):
+    import jslpsolver_b200 as J
+    from oracle import ref_model
+    jm = strip_timeouts(fx["model"])
+    res = J.Solve(jm)
+    bad = compare_solutions(res, fx["expects"])
+    if fx["file"] in ASSIGNMENT_UNCONFIRMED:
+        bad = [b for b in bad if b.startswith(("result", "feasible"))]
+    assert not bad, bad
+    ores = ref_model.Solve(jm, fast_cycles=True)
+    assert list(res.keys()) == list(ores.keys()), (res, ores)
+    for k in res:
+        assert res[k] == ores[k] or (res[k] != res[k] and ores[k] != ores[k]), (k, res[k], ores[k])
+
+
+@pytest.mark.parametrize("engine", list(ENGINES))
+@pytest.mark.parametrize("fx", [f for f in BUNDLE["fixtures"] if not (f["model"].get("ints") or f["model"].get("binaries"))],
+                         ids=lambda f: f["file"])
+def test_lp_fixture_tableau_bits(fx, engine):
+    """Continuous fixtures: pivot sequence, basis arrays, flags and every tableau bit."""
+    import jslpsolver_b200.tableau as T
+    from jslpsolver_b200.model import Model, presolve
+    jm = strip_timeouts(fx["model"])
+    m = Model().loadJson(jm)
+    if m.usePresolve:
+        pr = presolve(m)
+        if pr.isInfeasible:
+            pytest.skip("decided by presolve")
+        for v in pr.fixedVariables:
+            v.cost = 0
+    it = m.initial_tableau()
+    o = oracle_lp(it, check_cycles=m.checkForCycles)
+    o.simplex()
+    g = gpu_lp(it, ENGINES[engine])
+    g.model = m
+    g.simplex()
+    assert_lp_parity(g, o, fx["file"])
+
+
+# ------------------------------------------------------------------ seeded dense LPs
+@pytest.mark.parametrize("engine", list(ENGINES))
+@pytest.mark.parametrize("n,m,seed", [(5, 4, 1), (30, 20, 2), (64, 64, 3), (150, 120, 4), (333, 257, 5), (600, 500, 6)])
+def test_dense_packing_lp(n, m, seed, engine):
+    from jslpsolver_b200 import problems
+    it = problems.dense_packing_lp_tableau(n, m, seed)
+    o = oracle_lp(it)
+    o.simplex()
+    g = gpu_lp(it, ENGINES[engine])
+    g.simplex()
+    assert_lp_parity(g, o, f"dense {n}x{m}")
+    assert g.lastStatus.phase2_pivots > 0
+
+
+@pytest.mark.parametrize("engine", list(ENGINES))
+@pytest.mark.parametrize("n,m,seed", [(12, 9, 11), (40, 30, 12), (120, 80, 13), (260, 200, 14)])
+def test_mixed_lp_with_phase1(n, m, seed, engine, monkeypatch):
+    from jslpsolver_b200 import problems
+    from jslpsolver_b200.model import Model
+    mod = Model().loadJson(problems.mixed_lp_model(n, m, seed))
+    it = mod.initial_tableau()
+    o = oracle_lp(it)
+    o.simplex()
+    g = gpu_lp(it, ENGINES[engine])
+    g.simplex()
+    assert_lp_parity(g, o, f"mixed {n}x{m}")
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 7])
+def test_small_batches_and_cycle_rewind(batch):
+    """Cycle detection runs on the host over the drained log; with tiny batches the rewind
+    (snapshot + replay to the pivot before the repeat) is exercised at every offset."""
+    from jslpsolver_b200.model import Model
+    names = {"Cycling Fletcher.json", "Cycling introductory example.json", "Degenerate Max.json",
+             "Cycling steepest edge column selection.json", "Monster Problem.json"}
+    for fx in BUNDLE["fixtures"]:
+        if fx["file"] not in names:
+            continue
+        m = Model().loadJson(strip_timeouts(fx["model"]))
+        it = m.initial_tableau()
+        o = oracle_lp(it, check_cycles=m.checkForCycles)
+        o.simplex()
+        g = gpu_lp(it, 2, batch=batch)
+        g.model = m
+        g.simplex()
+        assert_lp_parity(g, o, f"{fx['file']} batch={batch}")
+
+
+def test_forced_cycle_is_detected_like_the_reference():
+    """Beale-type cycling LP under Dantzig + lowest-index ratio rule; whatever the reference
+    rules do with it (cycle or not), flags, counts and the stopping tableau must agree."""
+    from jslpsolver_b200.model import Model
+    model = {"optimize": "z", "opType": "max",
+             "constraints": {"c1": {"max": 0}, "c2": {"max": 0}, "c3": {"max": 1}},
+             "variables": {"x1": {"z": 0.75, "c1": 0.25, "c2": 0.5},
+                           "x2": {"z": -150, "c1": -60, "c2": -90},
+                           "x3": {"z": 0.02, "c1": -0.04, "c2": -0.02, "c3": 1},
+                           "x4": {"z": -6, "c1": 9, "c2": 3}}}
+    m = Model().loadJson(model)
+    it = m.initial_tableau()
+    for batch in (1, 2, 5, 256):
+        o = oracle_lp(it)
+        o.simplex()
+        g = gpu_lp(it, 2, batch=batch)
+        g.simplex()
+        assert_lp_parity(g, o, f"beale batch={batch}")
+
+
+# ------------------------------------------------------------------ seam primitives
+def test_pivot_save_restore_cuts_and_mip_scan():
+    from jslpsolver_b200 import problems
+    it = problems.dense_packing_lp_tableau(23, 17, seed=9)
+    ints = np.array([17 + j for j in range(0, 23, 2)], dtype=np.int32)
+    it.integerIndices = ints
+    o = oracle_lp(it)
+    g = gpu_lp(it, 2)
+    for (r, c) in [(3, 4), (7, 1), (1, 23), (17, 12)]:
+        o.pivot(r, c)
+        g.pivot(r, c)
+    assert same_bits(g.matrix2d(), o.matrix())
+    assert np.array_equal(g.varIndexByRow, o.maps()[0]) and np.array_equal(g.varIndexByCol, o.maps()[1])
+    o.simplex(); g.simplex()
+    assert_lp_parity(g, o, "after explicit pivots")
+    assert g.isIntegral() == o.is_integral()
+    iv, val = o.most_fractional()
+    mf = g.getMostFractionalVar()
+    assert (mf["index"] if mf["index"] is not None else -1) == iv and same_bits(mf["value"], val)
+    o.save(); g.save()
+    basic = int(o.maps()[0][2])          # a basic variable
+    nonbasic = int(o.maps()[1][3])       # a non-basic variable
+    cuts = [("min", basic, 1.0), ("max", nonbasic, 2.0), ("max", basic, 5.0)]
+    o.add_cuts(cuts); g.addCutConstraints(cuts)
+    assert g.height == o.state().height
+    assert same_bits(g.matrix2d(), o.matrix())
+    assert np.array_equal(g.varIndexByRow, o.maps()[0])
+    o.simplex(); g.simplex()
+    assert_lp_parity(g, o, "after cuts")
+    o.restore(); g.restore()
+    assert g.height == o.state().height and same_bits(g.matrix2d(), o.matrix())
+    st = o.apply_cuts(cuts[:2]); g.applyCuts(cuts[:2])
+    assert_lp_parity(g, o, "applyCuts")
+
+
+def test_row_capacity_growth():
+    from jslpsolver_b200 import problems
+    from jslpsolver_b200.tableau import GpuTableau
+    it = problems.dense_packing_lp_tableau(9, 6, seed=21)
+    o = oracle_lp(it)
+    g = GpuTableau(1e-8)
+    g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, row_capacity=7)
+    o.simplex(); g.simplex()
+    o.save(); g.save()
+    nb = [int(v) for v in o.maps()[1][1:6]]
+    cuts = [("max", v, 3.0) for v in nb] * 5
+    o.add_cuts(cuts); g.addCutConstraints(cuts)
+    assert same_bits(g.matrix2d(), o.matrix())
+    o.simplex(); g.simplex()
+    assert same_bits(g.matrix2d(), o.matrix())
+
+
+# ------------------------------------------------------------------ branch and cut
+@pytest.mark.parametrize("fx", [f for f in BUNDLE["fixtures"] if (f["model"].get("ints") or f["model"].get("binaries"))
+                                and f["file"] != "Vendor Selection.json"], ids=lambda f: f["file"])
+def test_mip_fixture_node_sequence(fx):
+    """Same pop order, same per-node outcomes, same final tableau as the reference's loop."""
+    import jslpsolver_b200 as J
+    from oracle import ref_model
+    jm = strip_timeouts(fx["model"])
+    osol = ref_model.solve_full(jm, fast_cycles=True, node_log=1 << 20)
+    if osol.tableau is None:
+        pytest.skip("decided by presolve")
+    gsol = J.Solve(jm, full=True)
+    gt = gsol._tableau
+    onl, gnl = osol.tableau.node_log(), gt.node_log()
+    assert gnl.shape == onl.shape, (gnl.shape, onl.shape)
+    for i in range(len(onl)):
+        a, b = gnl[i], onl[i]
+        ok = a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[4] == b[4] and a[5] == b[5] and a[7] == b[7]
+        ok = ok and same_bits(a[6], b[6]) and (not b[2] or same_bits(a[3], b[3]))
+        assert ok, f"node {i}: gpu={a.tolist()} oracle={b.tolist()}"
+    st = osol.state
+    assert gt.branchAndCutIterations == st.bncIterations
+    assert (gt.feasible, gt.bounded) == (bool(st.feasible), bool(st.bounded))
+    assert same_bits(gt.matrix2d(), osol.tableau.matrix())
+    assert np.array_equal(gt.varIndexByRow, osol.tableau.maps()[0])
+    assert [(a, b, float(c)) for a, b, c in gt.bestCuts] == [(a, b, float(c)) for a, b, c in osol.tableau.best_cuts()]

@@ -1,0 +1,97 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol that
+include/jslp_b200.h declares, the product front end builds the same initial tableau as the
+oracle's restatement on every golden fixture, and the product fails loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_bundle
+from helpers import strip_timeouts
+
+BUNDLE = load_bundle()
+
+
+def test_library_exports_every_declared_symbol():
+    from jslpsolver_b200 import _lib
+    L = _lib.load()
+    header = open(os.path.join(ROOT, "include", "jslp_b200.h")).read()
+    declared = set(re.findall(r"\b(jslp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"jslp_ctx", "jslp_tab"}
+    assert declared, "no declarations parsed"
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.jslp_abi_version() == 1
+
+
+def test_library_contains_sm100a_code():
+    import subprocess
+    from jslpsolver_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+@pytest.mark.parametrize("fx", BUNDLE["fixtures"] + BUNDLE["readme"], ids=lambda f: f["file"])
+def test_front_end_matches_oracle_front_end(fx, monkeypatch):
+    """Row/column order decides every tie-break: the upload source must be
+    identical, bit for bit, to the restated reference front end."""
+    import jslpsolver_b200.tableau as T
+    from jslpsolver_b200.model import Model, presolve
+    from oracle import ref_model
+
+    class NoDevice:  # the front end itself needs no GPU
+        def __init__(self, *a, **k):
+            pass
+    monkeypatch.setattr(T, "GpuTableau", NoDevice)
+    jm = strip_timeouts(fx["model"])
+    m = Model().loadJson(jm)
+    r = ref_model.RefModel().loadJson(jm)
+    pm = presolve(m)
+    inf, fixed = ref_model.presolve(r)
+    assert pm.isInfeasible == inf
+    assert sorted((v.id, float(x)) for v, x in pm.fixedVariables.items()) == sorted((v.id, float(x)) for v, x in fixed.items())
+    it = m.initial_tableau()
+    M, vr, vc, pr, rc = r.build_tableau()
+    assert np.array_equal(it.matrix, M)
+    assert np.array_equal(it.varIndexByRow, vr) and np.array_equal(it.varIndexByCol, vc)
+    assert it.optionalPriorities == pr and np.array_equal(it.optionalCosts, rc)
+    assert m.checkForCycles == r.checkForCycles and m.tolerance == r.tolerance
+    assert [v.index for v in m.integerVariables] == [v.index for v in r.integerVariables]
+
+
+def test_direct_tableau_equals_model_path(monkeypatch):
+    import jslpsolver_b200.tableau as T
+    from jslpsolver_b200 import problems
+    from jslpsolver_b200.model import Model
+
+    class NoDevice:
+        def __init__(self, *a, **k):
+            pass
+    monkeypatch.setattr(T, "GpuTableau", NoDevice)
+    it = Model().loadJson(problems.dense_packing_lp_model(7, 5, seed=3)).initial_tableau()
+    direct = problems.dense_packing_lp_tableau(7, 5, seed=3)
+    assert np.array_equal(it.matrix, direct.matrix)
+    assert np.array_equal(it.varIndexByRow, direct.varIndexByRow)
+    assert np.array_equal(it.varIndexByCol, direct.varIndexByCol)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must raise, never compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import jslpsolver_b200 as J
+    with pytest.raises(J.JslpError):
+        J.Solve(BUNDLE["readme"][0]["model"])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "jslpsolver_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/", "").lower() or f in (), (f, "mentions oracle")
