@@ -76,9 +76,16 @@ enum {
     JSLP_OPT_ENGINE = 1,       /* 0 = auto, 1 = two-kernel (select + update), 2 = fused step,
                                   3 = persistent fused, 4 = single-CTA resident            */
     JSLP_OPT_BATCH = 2,        /* pivots enqueued per host poll (default 256)              */
-    JSLP_OPT_PIVOT_LOG_CAP = 3 /* keep a host-side (row,col,leaving,entering) log, 0 = off */
+    JSLP_OPT_PIVOT_LOG_CAP = 3, /* keep a host-side (row,col,leaving,entering) log, 0 = off */
+    /* tuning / diagnostics of the fused pivot step (no effect on results) */
+    JSLP_OPT_STEP_VARIANT = 4, /* kernel instantiation: threads, occupancy, rows per pass, prefetch */
+    JSLP_OPT_GRID_PER_SM = 5,  /* CTAs per SM of the fused step, 0 = the variant's default        */
+    JSLP_OPT_LOOKAHEAD = 6,    /* 1 (default) = look-ahead ratio test, 0 = generic serial tail    */
+    JSLP_OPT_TIMELINE = 7      /* record a per-CTA timeline for the first N launches of a solve   */
 };
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
+/* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */
+int jslp_debug_timeline(jslp_tab *tab, int64_t *out, int64_t cap_values, int *launches, int *grid);
 
 /* Tableau state read by callers after simplex() (SURVEY.md 8b "State contract"). */
 typedef struct {

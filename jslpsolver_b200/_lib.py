@@ -10,6 +10,7 @@ from . import build as _build
 _LIB = None
 
 OPT_ENGINE, OPT_BATCH, OPT_PIVOT_LOG_CAP = 1, 2, 3
+OPT_STEP_VARIANT, OPT_GRID_PER_SM, OPT_LOOKAHEAD, OPT_TIMELINE = 4, 5, 6, 7
 ENGINE_AUTO, ENGINE_TWO_KERNEL, ENGINE_FUSED, ENGINE_PERSISTENT, ENGINE_RESIDENT = 0, 1, 2, 3, 4
 
 
@@ -59,6 +60,7 @@ SYMBOLS = [
     ("jslp_tab_destroy", None, [P]),
     ("jslp_tab_upload", C.c_int, [P, P, P, P, P, C.c_int, P, C.c_int, C.c_int, P]),
     ("jslp_tab_set_option", C.c_int, [P, C.c_int, C.c_double]),
+    ("jslp_debug_timeline", C.c_int, [P, P, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("jslp_simplex", C.c_int, [P, C.c_int, C.POINTER(LpStatus)]),
     ("jslp_phase1", C.c_int, [P, C.c_int, C.POINTER(LpStatus)]),
     ("jslp_phase2", C.c_int, [P, C.c_int, C.POINTER(LpStatus)]),

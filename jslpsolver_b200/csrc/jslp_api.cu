@@ -9,6 +9,7 @@
 //   * the branch-and-cut frontier (branch-and-cut.ts:54-199, min-heap.ts) -- see jslp_bnb.cuh
 #include "../../include/jslp_b200.h"
 #include "jslp_kernels.cuh"
+#include "jslp_node_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -36,6 +37,7 @@ struct jslp_ctx {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     int num_sms = 148;
+    int max_smem_optin = 48 * 1024;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -60,6 +62,43 @@ struct NodeLogEntry {
     double v[8];
 };
 
+// Host/device staging for batches of shared-memory-resident node LPs (k_node_batch).
+struct ResidentBufs {
+    CutDev *d_cuts = nullptr, *h_cuts = nullptr;
+    int *d_off = nullptr, *h_off = nullptr;
+    NodeResult *d_res = nullptr, *h_res = nullptr;
+    int4 *d_logs = nullptr, *h_logs = nullptr;
+    int cap_nodes = 0, cap_cuts = 0, log_cap = 0, smem_set = 0;
+    void release() {
+        cudaFree(d_cuts); cudaFree(d_off); cudaFree(d_res); cudaFree(d_logs);
+        cudaFreeHost(h_cuts); cudaFreeHost(h_off); cudaFreeHost(h_res); cudaFreeHost(h_logs);
+        d_cuts = h_cuts = nullptr; d_off = h_off = nullptr; d_res = h_res = nullptr; d_logs = h_logs = nullptr;
+        cap_nodes = cap_cuts = log_cap = 0;
+    }
+    int ensure(int n, int totc, int lc) {
+        if (n > cap_nodes || lc != log_cap) {
+            const int cn = std::max(64, std::max(n, cap_nodes) * 2);
+            cudaFree(d_off); cudaFree(d_res); cudaFree(d_logs);
+            cudaFreeHost(h_off); cudaFreeHost(h_res); cudaFreeHost(h_logs);
+            CK(cudaMalloc(&d_off, sizeof(int) * (size_t)(cn + 1)));
+            CK(cudaMallocHost(&h_off, sizeof(int) * (size_t)(cn + 1)));
+            CK(cudaMalloc(&d_res, sizeof(NodeResult) * (size_t)cn));
+            CK(cudaMallocHost(&h_res, sizeof(NodeResult) * (size_t)cn));
+            CK(cudaMalloc(&d_logs, sizeof(int4) * (size_t)cn * lc));
+            CK(cudaMallocHost(&h_logs, sizeof(int4) * (size_t)cn * lc));
+            cap_nodes = cn; log_cap = lc;
+        }
+        if (totc > cap_cuts) {
+            const int cc = std::max(1024, totc * 2);
+            cudaFree(d_cuts); cudaFreeHost(h_cuts);
+            CK(cudaMalloc(&d_cuts, sizeof(CutDev) * (size_t)cc));
+            CK(cudaMallocHost(&h_cuts, sizeof(CutDev) * (size_t)cc));
+            cap_cuts = cc;
+        }
+        return JSLP_OK;
+    }
+};
+
 struct jslp_tab {
     jslp_ctx *ctx = nullptr;
     TabDev hd{};            // host mirror of the device descriptor
@@ -80,6 +119,7 @@ struct jslp_tab {
     int isIntegralFlag = 0, bncIterations = 0;
     // options
     int engine = 0, batch = 256;
+    int variant = 0, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1;
     int64_t host_log_cap = 0;
     std::vector<int4> host_log;
     // graphs
@@ -88,6 +128,7 @@ struct jslp_tab {
     Saved saved;
     Snapshot snap;
     std::vector<NodeLogEntry> node_log;
+    ResidentBufs rbufs;
 };
 
 extern "C" const char *jslp_last_error(void) { return g_err.c_str(); }
@@ -107,6 +148,7 @@ extern "C" int jslp_ctx_create(int device, void *stream, jslp_ctx **out) {
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, device));
     c->num_sms = p.multiProcessorCount;
+    c->max_smem_optin = (int)p.sharedMemPerBlockOptin;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -233,10 +275,12 @@ extern "C" void jslp_tab_destroy(jslp_tab *t) {
     cudaFree(t->hd.M); cudaFree(t->hd.vrow); cudaFree(t->hd.vcol); cudaFree(t->hd.unres);
     cudaFree(t->hd.opt); cudaFree(t->hd.prow); cudaFree(t->hd.pcol); cudaFree(t->hd.optcoef);
     cudaFree(t->hd.plog); cudaFree(t->hd.optflag); cudaFree(t->hd.intpos);
+    cudaFree(t->hd.part); cudaFree(t->hd.dbg);
     cudaFree(t->d_T); cudaFree(t->d_rec); cudaFree(t->d_mip); cudaFree(t->d_cuts);
     cudaFreeHost(t->h_rec); cudaFreeHost(t->h_log); cudaFreeHost(t->h_mip); cudaFreeHost(t->h_cuts);
     free_saved(t->saved);
     free_snap(t->snap);
+    t->rbufs.release();
     delete t;
 }
 
@@ -308,34 +352,112 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
             t->host_log_cap = (int64_t)value;
             t->host_log.clear();
             return JSLP_OK;
+        case JSLP_OPT_STEP_VARIANT:
+            if (value < 0 || value >= 7) return fail(JSLP_E_INVALID, "step variant out of range");
+            t->variant = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_GRID_PER_SM:
+            if (value < 0 || value > 16) return fail(JSLP_E_INVALID, "grid per SM must be 0..16");
+            t->grid_per_sm = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_LOOKAHEAD:
+            t->lookahead = value != 0;
+            return JSLP_OK;
+        case JSLP_OPT_TIMELINE:
+            if (value < 0 || value > 4096) return fail(JSLP_E_INVALID, "timeline launches must be 0..4096");
+            t->timeline_cap = (int)value;
+            return JSLP_OK;
     }
     return fail(JSLP_E_INVALID, "unknown option");
 }
 
+// Debug: per-CTA timeline of the first `launches` pivot steps of the last solve.  8 int64 per CTA
+// per launch: globaltimer at start [ns], cycles to {row staged, rows updated, ticket taken, exit},
+// SM id, is-last-CTA, rows owned.
+extern "C" int jslp_debug_timeline(jslp_tab *t, int64_t *out, int64_t cap_values, int *launches, int *grid) {
+    if (!t || !launches || !grid) return fail(JSLP_E_INVALID, "NULL argument");
+    *launches = t->hd.dbg ? t->hd.dbg_cap : 0;
+    *grid = t->hd.dbg ? t->hd.dbg_grid : 0;
+    if (!out || !t->hd.dbg) return JSLP_OK;
+    const int64_t n = std::min<int64_t>(cap_values, (int64_t)8 * t->hd.dbg_grid * t->hd.dbg_cap);
+    CK(cudaSetDevice(t->ctx->device));
+    CK(cudaMemcpyAsync(out, t->hd.dbg, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, t->ctx->stream));
+    CK(cudaStreamSynchronize(t->ctx->stream));
+    return JSLP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
+// Instantiations of the fused step: <threads, min CTAs/SM, rows per pass, software prefetch>.
+typedef void (*step_fn_t)(const TabDev *, Rec *, int);
+struct StepVariant {
+    step_fn_t fn;
+    int threads, ctas_per_sm;
+    const char *name;
+};
+static const StepVariant STEP_VARIANTS[] = {
+    {k_pivot_step<256, 2, 8, false>, 256, 2, "t256 occ2 rc8"},
+    {k_pivot_step<256, 2, 4, true>, 256, 2, "t256 occ2 rc4 prefetch"},
+    {k_pivot_step<256, 4, 4, false>, 256, 4, "t256 occ4 rc4"},
+    {k_pivot_step<512, 1, 8, false>, 512, 1, "t512 occ1 rc8"},
+    {k_pivot_step<256, 3, 4, true>, 256, 3, "t256 occ3 rc4 prefetch"},
+    {k_pivot_step<128, 8, 4, false>, 128, 8, "t128 occ8 rc4"},
+    {k_pivot_step<256, 4, 2, true>, 256, 4, "t256 occ4 rc2 prefetch"},
+};
+static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VARIANTS[0]));
+
+static const StepVariant &step_variant(const jslp_tab *t) { return STEP_VARIANTS[t->variant]; }
+
 static int step_grid(const jslp_tab *t) {
-    int g = t->ctx->num_sms * 2;
+    const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : step_variant(t).ctas_per_sm;
+    int g = t->ctx->num_sms * per_sm;
     return std::max(1, std::min(g, t->rowcap));
+}
+
+// (re)allocates the buffers that depend on the step grid: look-ahead partials, debug timeline
+static int ensure_step_bufs(jslp_tab *t, int grid) {
+    if (grid > t->part_cap) {
+        CK(cudaStreamSynchronize(t->ctx->stream));
+        cudaFree(t->hd.part);
+        CK(cudaMalloc(&t->hd.part, sizeof(Part) * (size_t)grid));
+        t->part_cap = grid;
+    }
+    if (t->timeline_cap > 0 && (t->hd.dbg == nullptr || t->hd.dbg_grid != grid || t->hd.dbg_cap != t->timeline_cap)) {
+        CK(cudaStreamSynchronize(t->ctx->stream));
+        cudaFree(t->hd.dbg);
+        CK(cudaMalloc(&t->hd.dbg, sizeof(long long) * 8 * (size_t)grid * t->timeline_cap));
+        CK(cudaMemsetAsync(t->hd.dbg, 0, sizeof(long long) * 8 * (size_t)grid * t->timeline_cap, t->ctx->stream));
+        t->hd.dbg_grid = grid;
+        t->hd.dbg_cap = t->timeline_cap;
+    } else if (t->timeline_cap == 0 && t->hd.dbg) {
+        CK(cudaStreamSynchronize(t->ctx->stream));
+        cudaFree(t->hd.dbg);
+        t->hd.dbg = nullptr; t->hd.dbg_cap = 0;
+    }
+    return push_desc(t);
 }
 
 static int build_graphs(jslp_tab *t) {
     const int grid = step_grid(t);
     const int smem = t->stride * 8;
-    if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem) return JSLP_OK;
+    int rc = ensure_step_bufs(t, grid);
+    if (rc) return rc;
+    if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem && t->g_variant == t->variant)
+        return JSLP_OK;
     drop_graphs(t);
     cudaStream_t s = t->ctx->stream;
-    CK(cudaFuncSetAttribute(k_pivot_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const StepVariant &sv = step_variant(t);
+    CK(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     for (int mode = 0; mode < 2; mode++) {
         cudaGraph_t g;
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
         if (mode == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
             k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-            for (int i = 0; i < t->batch; i++) k_pivot_step<<<grid, STEP_THREADS, smem, s>>>(t->d_T, t->d_rec, 1);
+            for (int i = 0; i < t->batch; i++) sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 1);
         } else {  // two kernels per pivot
             for (int i = 0; i < t->batch; i++) {
                 k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-                k_pivot_step<<<grid, STEP_THREADS, smem, s>>>(t->d_T, t->d_rec, 0);
+                sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0);
             }
         }
         cudaError_t e = cudaStreamEndCapture(s, &g);
@@ -346,7 +468,7 @@ static int build_graphs(jslp_tab *t) {
         if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
         if (mode == 0) t->g_fused = ge; else t->g_simple = ge;
     }
-    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem;
+    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant;
     return JSLP_OK;
 }
 
@@ -432,12 +554,96 @@ static void fill_status(jslp_tab *t, jslp_lp_status *o, const Rec &r, int cycled
     o->gpu_ms = ms; o->kernel_launches = launches;
 }
 
+static size_t node_smem_bytes(int Hcap, int W, int *Ws_out);
+static int ensure_snapshot(jslp_tab *t);
+static void finish_lp_flags(jslp_tab *t, int only_phase, int cycled, const Rec &last);
+
+// Engine 4: the whole simplex() of a small tableau in ONE launch, tableau resident in shared
+// memory (k_node_batch with a single node and no cuts).  The result is written to the snapshot
+// buffers and adopted only if the pivot log shows no cycle; otherwise (or when the in-kernel pivot
+// cap is hit) *handled = false and the caller runs the HBM path on the untouched tableau.
+static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, bool timed, bool *handled) {
+    *handled = false;
+    jslp_ctx *ctx = t->ctx;
+    cudaStream_t s = ctx->stream;
+    int Ws = 0;
+    const size_t smem = node_smem_bytes(t->H, t->W, &Ws);
+    if (t->nOpt > 0 || smem > (size_t)ctx->max_smem_optin - 2048) return JSLP_OK;
+    int rc = ensure_snapshot(t);
+    if (rc) return rc;
+    const int log_cap = 2048;
+    rc = t->rbufs.ensure(1, 0, log_cap);
+    if (rc) return rc;
+    ResidentBufs &rb = t->rbufs;
+    const int64_t launches0 = ctx->launches;
+    if (timed) CK(cudaEventRecord(ctx->ev0, s));
+    rb.h_off[0] = 0; rb.h_off[1] = 0;
+    CK(cudaMemcpyAsync(rb.d_off, rb.h_off, sizeof(int) * 2, cudaMemcpyHostToDevice, s));
+    NodeBatchDev nb;
+    memset(&nb, 0, sizeof(nb));
+    nb.rootM = t->hd.M; nb.root_vrow = t->hd.vrow; nb.root_vcol = t->hd.vcol;
+    nb.cuts = rb.d_cuts; nb.cut_off = rb.d_off; nb.results = rb.d_res; nb.logs = rb.d_logs;
+    nb.wb_M = t->snap.M; nb.wb_vrow = t->snap.vrow; nb.wb_vcol = t->snap.vcol;
+    nb.H0 = t->H; nb.root_stride = t->stride; nb.first_index = t->lastElementIndex;
+    nb.Hcap = t->H; nb.Ws = Ws; nb.log_cap = log_cap; nb.max_pivots = log_cap - 2;
+    if ((int)smem > rb.smem_set) {
+        CK(cudaFuncSetAttribute(k_node_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rb.smem_set = (int)smem;
+    }
+    k_node_batch<<<1, NODE_THREADS, smem, s>>>(t->d_T, nb);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rb.h_res, rb.d_res, sizeof(NodeResult), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)log_cap, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const NodeResult r = rb.h_res[0];
+    if (r.overflow || r.log_n > log_cap) return JSLP_OK;
+    if (check_cycles) {
+        std::vector<long long> h1, h2;
+        int cs, cl;
+        for (int k = 0; k < r.log_n; k++) {
+            std::vector<long long> &h = ((rb.h_logs[k].x >> 30) & 1) ? h2 : h1;
+            h.push_back(((long long)rb.h_logs[k].z << 32) | (unsigned int)rb.h_logs[k].w);
+            if (cycle_hit(h, &cs, &cl)) return JSLP_OK;  // exact stop-before-repeat semantics: HBM path
+        }
+    }
+    // adopt the result
+    CK(cudaMemcpy2DAsync(t->hd.M, sizeof(double) * t->stride, t->snap.M, sizeof(double) * t->stride,
+                         sizeof(double) * t->W, t->H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vrow, t->snap.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vcol, t->snap.vcol, sizeof(int) * (size_t)t->W, cudaMemcpyDeviceToDevice, s));
+    float ms = 0.f;
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev1, s));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    }
+    if (t->host_log_cap > 0)  // executed pivots = every selection (the last selection always executes)
+        for (int k = 0; k < r.p1 + r.p2 && (int64_t)t->host_log.size() < t->host_log_cap; k++)
+            t->host_log.push_back(rb.h_logs[k]);
+    Rec last;
+    memset(&last, 0, sizeof(last));
+    last.status = r.status; last.p1 = r.p1; last.p2 = r.p2; last.unbounded_var = r.unbounded_var;
+    last.eval_raw = r.eval_raw;
+    t->bounded = 1;
+    finish_lp_flags(t, 0, 0, last);
+    fill_status(t, out, last, 0, 0, 0, ms, ctx->launches - launches0, 4);
+    *handled = true;
+    return JSLP_OK;
+}
+
 // Runs phase1 and/or phase2 on the device.  only_phase: 0 = simplex(), 1 = phase1(), 2 = phase2().
 static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status *out, bool timed) {
     jslp_ctx *ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    int rc = build_graphs(t);
+    int rc;
+    if (only_phase == 0 && (t->engine == 4 || (t->engine == 0 && (size_t)t->H * t->W <= 16384))) {
+        bool handled = false;
+        rc = run_lp_resident(t, check_cycles, out, timed, &handled);
+        if (rc || handled) return rc;
+    }
+    rc = build_graphs(t);
     if (rc) return rc;
     const int engine = (t->engine == 1) ? 1 : 2;
     cudaGraphExec_t graph = engine == 1 ? t->g_simple : t->g_fused;
@@ -451,6 +657,8 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     init.stop_at = -1;
     init.unbounded_var = -1;
     init.only_phase = only_phase;
+    init.lookahead = (engine == 2 && t->lookahead && t->nOpt == 0) ? 1 : 0;
+    init.next_c = -1;
     *t->h_rec = init;
     if (timed) CK(cudaEventRecord(ctx->ev0, s));
     CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
@@ -525,7 +733,13 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     }
 
-    // Tableau flag contract (simplex.ts:51-54,73-76,90-91,265-269,298-303,317-318)
+    finish_lp_flags(t, only_phase, cycled, last);
+    fill_status(t, out, last, cycled, cyc_start, cyc_len, ms, ctx->launches - launches0, engine);
+    return JSLP_OK;
+}
+
+// Tableau flag contract (simplex.ts:51-54,73-76,90-91,265-269,298-303,317-318)
+static void finish_lp_flags(jslp_tab *t, int only_phase, int cycled, const Rec &last) {
     if (cycled) {
         t->feasible = 0;
     } else if (last.status == ST_INFEASIBLE) {
@@ -542,8 +756,6 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
         t->bounded = 0;
         t->unboundedVar = last.unbounded_var;
     }
-    fill_status(t, out, last, cycled, cyc_start, cyc_len, ms, ctx->launches - launches0, engine);
-    return JSLP_OK;
 }
 
 extern "C" int jslp_simplex(jslp_tab *t, int check_cycles, jslp_lp_status *out) {
@@ -566,16 +778,25 @@ extern "C" int jslp_pivot(jslp_tab *t, int row, int col) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int smem = t->stride * 8;
-    CK(cudaFuncSetAttribute(k_pivot_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = step_grid(t);
+    int rc = ensure_step_bufs(t, grid);
+    if (rc) return rc;
+    const StepVariant &sv = step_variant(t);
+    CK(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     Rec init;
     memset(&init, 0, sizeof(init));
-    init.status = ST_RUNNING; init.phase = 2; init.stop_at = -1; init.unbounded_var = -1;
+    init.status = ST_RUNNING; init.phase = 2; init.stop_at = -1; init.unbounded_var = -1; init.next_c = -1;
     *t->h_rec = init;
     CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
     k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, row, col);
-    k_pivot_step<<<step_grid(t), STEP_THREADS, smem, s>>>(t->d_T, t->d_rec, 0);
+    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0);
     ctx->launches += 2;
     CK(cudaGetLastError());
+    if (t->host_log_cap > 0) {  // explicit pivots are part of the executed-pivot log
+        CK(cudaMemcpyAsync(t->h_log, t->hd.plog, sizeof(int4), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if ((int64_t)t->host_log.size() < t->host_log_cap) t->host_log.push_back(t->h_log[0]);
+    }
     CK(cudaStreamSynchronize(s));
     return JSLP_OK;
 }

@@ -1,19 +1,32 @@
 // jslpsolver_b200/csrc/jslp_bnb.cuh -- branch-and-cut frontier manager (included by jslp_api.cu).
 //
 // Replaces BranchAndCutService.branchAndCut (branch-and-cut.ts:54-199) and BranchMinHeap
-// (min-heap.ts).  The node order is the reference's: best-first on relaxedEvaluation, most
-// recently pushed first on ties.  Each node LP is a pure function of (root snapshot, cut list)
-// (SURVEY.md 3.8), evaluated on the device by restore -> add cuts -> simplex; the frontier and the
-// commit decisions stay on the host because they are a few hundred bytes per node.
+// (min-heap.ts).  The commit order is the reference's: best-first on relaxedEvaluation, most
+// recently pushed first on ties.  A node's LP result is a pure function of (root snapshot, cut
+// list), so the frontier is evaluated speculatively: every round takes the next K
+// open nodes in exact pop order, evaluates them together on the device (one CTA per node when the
+// tableau fits shared memory, else one after the other on the HBM path; sharded round-robin over
+// ranks with an all-gather of the 128-byte summaries when n_ranks > 1), then COMMITS results
+// sequentially in pop order exactly as the reference loop would.  A popped node without a cached
+// result ends the round.  Speculation that is never popped is wasted work, never wrong work.
 #pragma once
 
+#include <map>
 #include <memory>
 
 namespace jslp_bnb {
 
+struct NodeEval {  // what the commit loop needs from one node LP
+    bool valid = false;
+    int feasible = 0, bounded = 1, optimal = 0, is_integral = 0, branch_var = -1, pivots = 0;
+    double evaluation = 0, branch_value = 0;
+    double opt0[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // optionalObjectives[o].reducedCosts[0]
+};
+
 struct Branch {
     double relaxedEvaluation;
     std::vector<jslp_cut> cuts;
+    NodeEval ev;  // cached speculative result
 };
 
 // Total order of min-heap.ts:43-49: lower relaxedEvaluation first, then higher seq (LIFO).
@@ -29,8 +42,8 @@ struct Frontier {
         return a.seq > b.seq;
     }
     bool empty() const { return h.empty(); }
-    void push(std::unique_ptr<Branch> br) {
-        h.push_back(Entry{std::move(br), seqCounter++});
+    void push_entry(Entry e) {
+        h.push_back(std::move(e));
         size_t i = h.size() - 1;
         while (i > 0) {
             const size_t p = (i - 1) / 2;
@@ -39,9 +52,10 @@ struct Frontier {
             i = p;
         }
     }
-    std::unique_ptr<Branch> pop() {
-        std::unique_ptr<Branch> top = std::move(h[0].b);
-        h[0] = std::move(h.back());
+    void push(std::unique_ptr<Branch> br) { push_entry(Entry{std::move(br), seqCounter++}); }
+    Entry pop_entry() {
+        Entry top = std::move(h[0]);
+        if (h.size() > 1) h[0] = std::move(h.back());
         h.pop_back();
         size_t i = 0;
         const size_t n = h.size();
@@ -57,96 +71,226 @@ struct Frontier {
     }
 };
 
+static const int WIRE_DOUBLES = 16;  // all-gather record per node (128 bytes)
+static void to_wire(const NodeEval &e, double *w) {
+    w[0] = e.valid; w[1] = e.feasible; w[2] = e.bounded; w[3] = e.optimal; w[4] = e.is_integral;
+    w[5] = e.branch_var; w[6] = e.pivots; w[7] = e.evaluation;
+    memcpy(&w[7], &e.evaluation, 8);
+    memcpy(&w[8], &e.branch_value, 8);
+    for (int o = 0; o < 7; o++) memcpy(&w[9 + o], &e.opt0[o], 8);
+}
+static void from_wire(NodeEval &e, const double *w) {
+    e.valid = w[0] != 0; e.feasible = (int)w[1]; e.bounded = (int)w[2]; e.optimal = (int)w[3];
+    e.is_integral = (int)w[4]; e.branch_var = (int)w[5]; e.pivots = (int)w[6];
+    memcpy(&e.evaluation, &w[7], 8);
+    memcpy(&e.branch_value, &w[8], 8);
+    for (int o = 0; o < 7; o++) memcpy(&e.opt0[o], &w[9 + o], 8);
+}
+
 }  // namespace jslp_bnb
+
+// ---- node evaluation back-ends ---------------------------------------------------------------
+// HBM path: applyCuts (branch-and-cut.ts:33-52) in place, exactly as the reference does it.
+static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check_cycles, jslp_bnb::NodeEval &ev) {
+    jslp_lp_status st;
+    int rc = jslp_restore(t);
+    if (rc) return rc;
+    rc = jslp_add_cuts(t, b.cuts.data(), (int)b.cuts.size());
+    if (rc) return rc;
+    const double prevBest = t->bestPossibleEval;
+    const int prevIters = t->simplexIters;
+    rc = run_lp(t, 0, check_cycles, &st, false);
+    if (rc) return rc;
+    // simplexIters / bestPossibleEval are frontier state: the commit loop owns them
+    ev.optimal = t->simplexIters != prevIters;
+    t->simplexIters = prevIters;
+    t->bestPossibleEval = prevBest;
+    ev.valid = true;
+    ev.feasible = t->feasible; ev.bounded = t->bounded; ev.evaluation = t->evaluation;
+    ev.pivots = st.phase1_pivots + st.phase2_pivots;
+    ev.is_integral = 0; ev.branch_var = -1; ev.branch_value = 0;
+    if (ev.feasible) {
+        MipOut mo;
+        rc = mip_scan(t, &mo);
+        if (rc) return rc;
+        ev.is_integral = mo.is_integral; ev.branch_var = mo.var_index; ev.branch_value = mo.value;
+        if (t->nOpt > 0) {
+            std::vector<double> opt((size_t)t->nOpt * t->W);
+            rc = jslp_download(t, nullptr, nullptr, nullptr, nullptr, nullptr, opt.data(), nullptr, nullptr);
+            if (rc) return rc;
+            for (int o = 0; o < t->nOpt && o < 7; o++) ev.opt0[o] = opt[(size_t)o * t->W];
+        }
+    }
+    return JSLP_OK;
+}
+
+static size_t node_smem_bytes(int Hcap, int W, int *Ws_out) {
+    const int Ws = (W & 1) ? W : W + 1;  // odd row stride: conflict-free column walks
+    if (Ws_out) *Ws_out = Ws;
+    return sizeof(double) * ((size_t)Hcap * Ws + 2 * (size_t)Ws + Hcap) + sizeof(int) * ((size_t)Hcap + W) + 16;
+}
+
+static bool resident_fits(const jslp_tab *t, int Hcap) {
+    return t->nOpt == 0 && node_smem_bytes(Hcap, t->W, nullptr) <= (size_t)t->ctx->max_smem_optin - 2048;
+}
+
+// Evaluates nodes[0..n) with one CTA each (k_node_batch).  Nodes whose log shows a cycle or that
+// hit the in-kernel pivot cap are re-evaluated on the HBM path (exact cycle semantics there).
+static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int n, int check_cycles) {
+    jslp_ctx *ctx = t->ctx;
+    cudaStream_t s = ctx->stream;
+    ResidentBufs &rb = t->rbufs;
+    int maxc = 0, totc = 0;
+    for (int i = 0; i < n; i++) {
+        maxc = std::max(maxc, (int)nodes[i]->cuts.size());
+        totc += (int)nodes[i]->cuts.size();
+    }
+    const int Hcap = t->saved.H + maxc;
+    int Ws = 0;
+    const size_t smem = node_smem_bytes(Hcap, t->W, &Ws);
+    const int log_cap = 512;
+    int rc = rb.ensure(n, totc, log_cap);
+    if (rc) return rc;
+    int off = 0;
+    for (int i = 0; i < n; i++) {
+        rb.h_off[i] = off;
+        for (const jslp_cut &c : nodes[i]->cuts) {
+            rb.h_cuts[off].type = c.type; rb.h_cuts[off].var_index = c.var_index; rb.h_cuts[off].value = c.value;
+            off++;
+        }
+    }
+    rb.h_off[n] = off;
+    if (totc > 0) CK(cudaMemcpyAsync(rb.d_cuts, rb.h_cuts, sizeof(CutDev) * (size_t)totc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(rb.d_off, rb.h_off, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
+    NodeBatchDev nb;
+    memset(&nb, 0, sizeof(nb));
+    nb.rootM = t->saved.M; nb.root_vrow = t->saved.vrow; nb.root_vcol = t->saved.vcol;
+    nb.cuts = rb.d_cuts; nb.cut_off = rb.d_off; nb.results = rb.d_res; nb.logs = rb.d_logs;
+    nb.H0 = t->saved.H; nb.root_stride = t->stride; nb.first_index = t->saved.lastElementIndex;
+    nb.Hcap = Hcap; nb.Ws = Ws; nb.log_cap = log_cap; nb.max_pivots = 100000;
+    if ((int)smem > rb.smem_set) {
+        CK(cudaFuncSetAttribute(k_node_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rb.smem_set = (int)smem;
+    }
+    k_node_batch<<<n, NODE_THREADS, smem, s>>>(t->d_T, nb);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rb.h_res, rb.d_res, sizeof(NodeResult) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (check_cycles)
+        CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)n * log_cap, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; i++) {
+        const NodeResult &r = rb.h_res[i];
+        jslp_bnb::NodeEval &ev = nodes[i]->ev;
+        bool redo = r.overflow != 0;
+        if (!redo && check_cycles) {
+            std::vector<long long> h1, h2;
+            int cs, cl;
+            const int4 *lg = rb.h_logs + (size_t)i * log_cap;
+            for (int k = 0; k < r.log_n && k < log_cap && !redo; k++) {
+                std::vector<long long> &h = ((lg[k].x >> 30) & 1) ? h2 : h1;
+                h.push_back(((long long)lg[k].z << 32) | (unsigned int)lg[k].w);
+                if (cycle_hit(h, &cs, &cl)) redo = true;
+            }
+        }
+        if (redo) {
+            rc = eval_node_streaming(t, *nodes[i], check_cycles, ev);
+            if (rc) return rc;
+            continue;
+        }
+        ev.valid = true;
+        ev.pivots = r.p1 + r.p2;
+        ev.optimal = r.status == ST_OPTIMAL;
+        ev.bounded = r.status != ST_UNBOUNDED;
+        ev.feasible = r.status == ST_OPTIMAL || r.status == ST_UNBOUNDED;
+        if (r.status == ST_OPTIMAL) {
+            const double roundingCoeff = js_round_h(1 / t->precision);
+            ev.evaluation = js_round_h((2.220446049250313e-16 + r.eval_raw) * roundingCoeff) / roundingCoeff;
+        } else if (r.status == ST_UNBOUNDED) {
+            ev.evaluation = -INFINITY;
+        } else {
+            ev.evaluation = t->evaluation;  // stale, unused when infeasible
+        }
+        ev.is_integral = r.is_integral; ev.branch_var = r.branch_var; ev.branch_value = r.branch_value;
+    }
+    return JSLP_OK;
+}
 
 extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_bnb_status *out,
                                    jslp_cut *best_cuts, int best_cuts_cap) {
     using namespace jslp_bnb;
     if (!t || !opts) return fail(JSLP_E_INVALID, "NULL argument");
     if (t->n_int <= 0) return fail(JSLP_E_INVALID, "branch_and_cut needs integer variables (upload int_var_indices)");
+    const int n_ranks = std::max(1, opts->n_ranks), rank = opts->rank;
+    if (n_ranks > 1 && !opts->all_gather) return fail(JSLP_E_INVALID, "n_ranks > 1 needs an all_gather hook");
+    if (n_ranks > 1 && t->nOpt > 7) return fail(JSLP_E_UNSUPPORTED, "more than 7 optional objectives across ranks");
     jslp_ctx *ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
 
     Frontier branches;
-    int iterations = 0;
+    int iterations = 0, rounds = 0;
     const double tolerance = opts->tolerance;
+    const int check_cycles = opts->check_cycles;
     bool toleranceFlag = true;
     double bestEvaluation = INFINITY;
-    std::unique_ptr<Branch> bestBranch;
+    std::unique_ptr<Branch> bestBranch, lastCommitted;
     std::vector<double> bestOpt((size_t)t->nOpt, INFINITY);
-    std::vector<double> optNow((size_t)std::max(1, t->nOpt) * t->W);
     int64_t pivots = 0, nodes = 0;
     t->node_log.clear();
     t->saved.valid = false;
-    bool early_return = false;
+    t->isIntegralFlag = 0;
+    bool early_return = false, speculated = false;
+    int K = opts->max_spec_batch > 0 ? opts->max_spec_batch : 16;  // any width commits in the same order
+    std::vector<double> wire;
 
-    branches.push(std::unique_ptr<Branch>(new Branch{-INFINITY, {}}));
-    while (!branches.empty() && toleranceFlag) {
-        if (opts->max_nodes > 0 && iterations >= opts->max_nodes) break;
-        const double acceptableThreshold =
-            opts->is_minimization ? t->bestPossibleEval * (1 + tolerance) : t->bestPossibleEval * (1 - tolerance);
-        if (tolerance > 0 && bestEvaluation < acceptableThreshold) toleranceFlag = false;
-
-        std::unique_ptr<Branch> active = branches.pop();
-        if (active->relaxedEvaluation > bestEvaluation) continue;
-
-        jslp_lp_status st;
-        int rc = jslp_restore(t);
-        if (rc) return rc;
-        rc = jslp_add_cuts(t, active->cuts.data(), (int)active->cuts.size());
-        if (rc) return rc;
-        rc = run_lp(t, 0, opts->check_cycles, &st, false);
-        if (rc) return rc;
+    // commits one evaluated node exactly like one iteration of branch-and-cut.ts:89-192
+    auto commit = [&](std::unique_ptr<Branch> active) -> int {
+        const NodeEval ev = active->ev;
         iterations++;
-        nodes++;
-        pivots += st.phase1_pivots + st.phase2_pivots;
-
-        NodeLogEntry nl;
-        nl.v[0] = iterations; nl.v[1] = (double)active->cuts.size(); nl.v[2] = t->feasible;
-        nl.v[3] = t->evaluation; nl.v[4] = -1; nl.v[5] = -1; nl.v[6] = 0;
-        nl.v[7] = st.phase1_pivots + st.phase2_pivots;
-
-        if (!t->feasible) { t->node_log.push_back(nl); continue; }
-        const double evaluation = t->evaluation;
-        if (evaluation > bestEvaluation) { t->node_log.push_back(nl); continue; }
-
-        if (t->nOpt > 0) {
-            rc = jslp_download(t, nullptr, nullptr, nullptr, nullptr, nullptr, optNow.data(), nullptr, nullptr);
-            if (rc) return rc;
+        t->feasible = ev.feasible; t->bounded = ev.bounded;
+        if (ev.feasible) t->evaluation = ev.evaluation;
+        if (ev.optimal) {  // setEvaluation + simplexIters (tableau.ts:420-430, simplex.ts:266-267)
+            if (t->simplexIters == 0) t->bestPossibleEval = ev.evaluation;
+            t->simplexIters += 1;
         }
+        NodeLogEntry nl;
+        nl.v[0] = iterations; nl.v[1] = (double)active->cuts.size(); nl.v[2] = ev.feasible;
+        nl.v[3] = t->evaluation; nl.v[4] = -1; nl.v[5] = -1; nl.v[6] = 0; nl.v[7] = ev.pivots;
+        auto done = [&](std::unique_ptr<Branch> keep) {
+            t->node_log.push_back(nl);
+            lastCommitted = std::move(keep);
+        };
+        if (!ev.feasible) { done(std::move(active)); return 0; }
+        const double evaluation = ev.evaluation;
+        if (evaluation > bestEvaluation) { done(std::move(active)); return 0; }
         if (evaluation == bestEvaluation) {  // branch-and-cut.ts:107-127
             bool worse = true;
             for (int o = 0; o < t->nOpt; o++) {
-                const double v = optNow[(size_t)o * t->W];
-                if (v > bestOpt[o]) break;
-                if (v < bestOpt[o]) { worse = false; break; }
+                if (ev.opt0[o] > bestOpt[o]) break;
+                if (ev.opt0[o] < bestOpt[o]) { worse = false; break; }
             }
-            if (worse) { t->node_log.push_back(nl); continue; }
+            if (worse) { done(std::move(active)); return 0; }
         }
-
-        MipOut mo;
-        rc = mip_scan(t, &mo);
-        if (rc) return rc;
-        if (mo.is_integral) {
+        if (ev.is_integral) {
             nl.v[4] = 1;
-            t->node_log.push_back(nl);
             t->isIntegralFlag = 1;
-            if (iterations == 1) { early_return = true; break; }
+            if (iterations == 1) { t->node_log.push_back(nl); early_return = true; return 1; }
             bestEvaluation = evaluation;
-            for (int o = 0; o < t->nOpt; o++) bestOpt[o] = optNow[(size_t)o * t->W];
-            bestBranch = std::move(active);
+            for (int o = 0; o < t->nOpt; o++) bestOpt[o] = ev.opt0[o];
+            t->node_log.push_back(nl);
+            bestBranch.reset(new Branch{active->relaxedEvaluation, active->cuts, NodeEval()});
+            lastCommitted = std::move(active);
         } else {
-            if (iterations == 1) {
-                rc = jslp_save(t);
+            if (iterations == 1) {  // snapshot = optimal root tableau (branch-and-cut.ts:155-157)
+                int rc = jslp_save(t);
                 if (rc) return rc;
             }
-            const int varIndex = mo.var_index;
-            const double value = mo.value;
+            const int varIndex = ev.branch_var;
+            const double value = ev.branch_value;
             nl.v[4] = 0; nl.v[5] = varIndex; nl.v[6] = value;
-            t->node_log.push_back(nl);
-            std::unique_ptr<Branch> high(new Branch{evaluation, {}}), low(new Branch{evaluation, {}});
+            std::unique_ptr<Branch> high(new Branch{evaluation, {}, NodeEval()}), low(new Branch{evaluation, {}, NodeEval()});
             for (const jslp_cut &cut : active->cuts) {  // branch-and-cut.ts:166-179
                 if (cut.var_index == varIndex) {
                     if (cut.type == 0) low->cuts.push_back(cut); else high->cuts.push_back(cut);
@@ -159,23 +303,99 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             low->cuts.push_back(jslp_cut{1, varIndex, std::floor(value)});
             branches.push(std::move(high));
             branches.push(std::move(low));
+            done(std::move(active));
+        }
+        return 0;
+    };
+
+    branches.push(std::unique_ptr<Branch>(new Branch{-INFINITY, {}, NodeEval()}));
+    bool stop = false;
+    while (!stop && !branches.empty() && toleranceFlag) {
+        // ---- speculate: evaluate the next K un-evaluated open nodes in pop order ---------------
+        const int width = iterations == 0 ? 1 : K;  // the root decides everything: alone
+        std::vector<Frontier::Entry> taken;
+        std::vector<Branch *> todo;
+        while (!branches.empty() && (int)todo.size() < width) {
+            Frontier::Entry e = branches.pop_entry();
+            // nodes that will be skipped at pop (branch-and-cut.ts:90-92) stay in the heap -- their pop
+            // still consumes a loop iteration of the reference -- but are never evaluated
+            if (!(e.b->relaxedEvaluation > bestEvaluation) && !e.b->ev.valid) todo.push_back(e.b.get());
+            taken.push_back(std::move(e));
+        }
+        if (!todo.empty()) {
+            rounds++;
+            std::vector<Branch *> mine;
+            int maxc = 0;
+            for (size_t i = 0; i < todo.size(); i++)
+                if ((int)(i % n_ranks) == rank) {
+                    mine.push_back(todo[i]);
+                    maxc = std::max(maxc, (int)todo[i]->cuts.size());
+                }
+            const bool resident = iterations > 0 && t->saved.valid && t->engine != 1 && t->engine != 2 &&
+                                  resident_fits(t, t->saved.H + maxc);
+            if (resident && !mine.empty()) {
+                int rc = eval_nodes_resident(t, mine.data(), (int)mine.size(), check_cycles);
+                if (rc) return rc;
+            } else {
+                for (Branch *b : mine) {
+                    int rc = eval_node_streaming(t, *b, check_cycles, b->ev);
+                    if (rc) return rc;
+                }
+            }
+            nodes += (int64_t)mine.size();
+            if (todo.size() > 1) speculated = true;
+            if (n_ranks > 1) {  // all-gather the summaries: rank-major blocks of `per` records
+                const int per = (int)((todo.size() + n_ranks - 1) / n_ranks);
+                wire.assign((size_t)per * n_ranks * WIRE_DOUBLES, 0.0);
+                for (size_t j = 0; j < mine.size(); j++)
+                    to_wire(mine[j]->ev, &wire[((size_t)rank * per + j) * WIRE_DOUBLES]);
+                int rc = opts->all_gather(opts->user, wire.data(), (int64_t)per * WIRE_DOUBLES * 8);
+                if (rc) return fail(JSLP_E_INVALID, "all_gather hook failed");
+                for (size_t i = 0; i < todo.size(); i++)
+                    from_wire(todo[i]->ev, &wire[((size_t)(i % n_ranks) * per + i / n_ranks) * WIRE_DOUBLES]);
+            }
+        }
+        for (auto &e : taken) branches.push_entry(std::move(e));  // original seq: order unchanged
+
+        // ---- commit sequentially in the reference's exact order ---------------------------------
+        while (!branches.empty() && toleranceFlag) {
+            if (opts->max_nodes > 0 && iterations >= opts->max_nodes) { stop = true; break; }
+            const double acceptableThreshold = opts->is_minimization ? t->bestPossibleEval * (1 + tolerance)
+                                                                     : t->bestPossibleEval * (1 - tolerance);
+            // the reference checks the tolerance BEFORE popping, and still processes that pop
+            const bool tolHit = tolerance > 0 && bestEvaluation < acceptableThreshold;
+            if (branches.h[0].b->relaxedEvaluation <= bestEvaluation && !branches.h[0].b->ev.valid) break;  // next round
+            if (tolHit) toleranceFlag = false;
+            Frontier::Entry e = branches.pop_entry();
+            if (e.b->relaxedEvaluation > bestEvaluation) continue;
+            pivots += e.b->ev.pivots;
+            int rc = commit(std::move(e.b));
+            if (rc < 0) return rc;
+            if (rc == 1) { stop = true; break; }
         }
     }
 
+    // Final tableau: the reference re-solves the winner (branch-and-cut.ts:195-197); without a
+    // winner it is left at the last evaluated node.  In place on the HBM path.
     int n_best = 0;
-    if (!early_return && bestBranch) {  // branch-and-cut.ts:195-197
-        jslp_lp_status st;
-        int rc = jslp_restore(t);
-        if (rc) return rc;
-        rc = jslp_add_cuts(t, bestBranch->cuts.data(), (int)bestBranch->cuts.size());
-        if (rc) return rc;
-        rc = run_lp(t, 0, opts->check_cycles, &st, false);
-        if (rc) return rc;
-        nodes++;
-        pivots += st.phase1_pivots + st.phase2_pivots;
-        n_best = (int)bestBranch->cuts.size();
-        if (best_cuts)
-            for (int i = 0; i < n_best && i < best_cuts_cap; i++) best_cuts[i] = bestBranch->cuts[i];
+    if (!early_return) {
+        const Branch *fin = bestBranch ? bestBranch.get() : lastCommitted.get();
+        if (fin && (bestBranch || iterations > 1)) {
+            NodeEval ev;
+            int rc = eval_node_streaming(t, *fin, check_cycles, ev);
+            if (rc) return rc;
+            nodes++;
+            if (bestBranch) {
+                pivots += ev.pivots;
+                if (ev.optimal) t->simplexIters += 1;
+            }
+        }
+        (void)speculated;
+        if (bestBranch) {
+            n_best = (int)bestBranch->cuts.size();
+            if (best_cuts)
+                for (int i = 0; i < n_best && i < best_cuts_cap; i++) best_cuts[i] = bestBranch->cuts[i];
+        }
     }
     t->bncIterations = iterations;
 
@@ -186,7 +406,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
     if (out) {
         memset(out, 0, sizeof(*out));
         out->feasible = t->feasible; out->bounded = t->bounded; out->is_integral = t->isIntegralFlag;
-        out->iterations = iterations; out->n_best_cuts = n_best; out->rounds = iterations;
+        out->iterations = iterations; out->n_best_cuts = n_best; out->rounds = rounds;
         out->nodes_evaluated = nodes; out->pivots = pivots; out->evaluation = t->evaluation;
         out->best_possible_eval = t->bestPossibleEval; out->gpu_ms = ms;
         out->kernel_launches = ctx->launches - launches0;

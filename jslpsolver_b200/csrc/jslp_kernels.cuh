@@ -27,6 +27,8 @@ namespace jslp {
 
 enum { ST_RUNNING = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_P1_DONE = 4 };
 
+struct Part;
+
 // Device-resident description of one tableau (kernels read it through a pointer so that a
 // captured CUDA graph stays valid when H grows or buffers are re-allocated).
 struct TabDev {
@@ -41,10 +43,23 @@ struct TabDev {
     int4 *plog;            // per-batch pivot log (row, col, leaving var, entering var)
     unsigned char *optflag; // scratch [W] for the optional-objective tie-break lists
     int *intpos;           // position in model.integerVariables by var index, -1 otherwise [n_index]
+    Part *part;            // per-CTA look-ahead ratio-test partials [grid]
+    long long *dbg;        // optional per-CTA timeline (8 x int64 per CTA per launch) or nullptr
     int W, H, stride, rowcap;
     int nOpt, n_index, plog_cap;
     int batch_size, use_partial;  // phase-2 partial pricing (simplex.ts:118-127)
+    int dbg_cap, dbg_grid;
     double prec;
+};
+
+// Look-ahead partial of one CTA: ratio test (simplex.ts:271-296) over its own freshly updated rows
+// against the NEXT entering column, so the last CTA only has to reduce gridDim.x of these.
+struct Part {
+    double minq;        // smallest admissible quotient among this CTA's rows (INF = none)
+    int minr;           // row of minq (INT_MAX = none)
+    int dmin;           // first degenerate row (INT_MAX = none)
+    int cnt;            // rows with a non-zero pivot-column entry (for the lazy flush flag)
+    int pad;
 };
 
 // Pivot record: the decision carried from one launch to the next.
@@ -62,7 +77,10 @@ struct Rec {
     int unbounded_var;
     int only_phase;  // 0 = simplex(), 1 = phase1() only, 2 = phase2() only
     unsigned int ticket;
-    int pad;
+    int lookahead;   // host switch: 1 = the tail also prices the pivot after next
+    int next_c;      // entering column of the NEXT pivot, priced on the cost row as it will be after
+                     // the staged pivot: -1 unknown (generic tail), 0 none (optimal), >0 column
+    int next_neg;    // its isReducedCostNegative
     double q;        // raw pivot element
     double eval_raw; // matrix[0] at exit
 };
@@ -76,6 +94,10 @@ struct MipOut {
 __device__ __forceinline__ bool nz16(double v) { return !(v >= -1e-16 && v <= 1e-16); }
 
 __device__ __forceinline__ double ldg_cg(const double *p) { return __ldcg(p); }
+// GLOBAL = tableau lives in HBM/L2 and may just have been rewritten by other CTAs (bypass L1);
+// !GLOBAL = tableau lives in this CTA's shared memory (generic pointers, plain loads).
+template <bool GLOBAL>
+__device__ __forceinline__ double ldt(const double *p) { return GLOBAL ? __ldcg(p) : *p; }
 
 // JS Math.round: nearest, ties toward +inf
 __device__ __forceinline__ double js_round(double x) {
@@ -218,14 +240,15 @@ struct SelSmem {
 // Stage pivot (rstar, cstar): raw pivot row -> prow, optional pivot-column entries, label swap,
 // pivot log, record.  `cnt` = number of rows r (incl. row 0 and rstar) with a non-zero
 // pivot-column entry; pcol must already be staged.
+template <bool GLOBAL>
 __device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar, int cstar,
                                 int isneg, int cnt) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const double *prowsrc = T.M + (size_t)rstar * T.stride;
-    for (int c = tid; c < T.stride; c += NT) T.prow[c] = c < T.W ? ldg_cg(prowsrc + c) : 0.0;
-    for (int o = tid; o < T.nOpt; o += NT) T.optcoef[o] = ldg_cg(T.opt + (size_t)o * T.stride + cstar);
+    for (int c = tid; c < T.stride; c += NT) T.prow[c] = c < T.W ? ldt<GLOBAL>(prowsrc + c) : 0.0;
+    for (int o = tid; o < T.nOpt; o += NT) T.optcoef[o] = ldt<GLOBAL>(T.opt + (size_t)o * T.stride + cstar);
     if (tid == 0) {
-        const double q = ldg_cg(prowsrc + cstar);
+        const double q = ldt<GLOBAL>(prowsrc + cstar);
         const int leaving = T.vrow[rstar], entering = T.vcol[cstar];
         if (rec->log_n < T.plog_cap) T.plog[rec->log_n] = make_int4(rstar | (phase == 2 ? (1 << 30) : 0), cstar, leaving, entering);
         rec->log_n += 1;
@@ -238,12 +261,14 @@ __device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar,
         rec->is_neg = isneg;
         rec->flush = (cnt - (nz16(q) ? 1 : 0)) > 0;
         rec->has_pivot = 1;
+        rec->next_c = -1;  // the pivot after this one has not been priced
     }
 }
 
 // One CTA decides the next pivot from the tableau as it stands in L2/HBM (phase1: simplex.ts:
 // 38-76, phase2: 129-303) and stages it.  All tableau reads bypass L1 (__ldcg): in the fused
 // kernel this runs after other CTAs have just rewritten the tableau.
+template <bool GLOBAL>
 __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int W = T.W, H = T.H;
@@ -259,13 +284,13 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
         const VI init = {-prec, INT_MAX};
         VI b = init;
         for (int r = 1 + tid; r < H; r += NT) {
-            const double v = ldg_cg(M + r * stride);
+            const double v = ldt<GLOBAL>(M + r * stride);
             if (v < b.v) { b.v = v; b.i = r; }
         }
         b = block_reduce_vi<true>(b, init, s.red);
         if (b.i == INT_MAX) {  // feasible (simplex.ts:51-54)
             if (only_phase == 1) {
-                if (tid == 0) { rec->status = ST_P1_DONE; rec->has_pivot = 0; rec->eval_raw = ldg_cg(M); }
+                if (tid == 0) { rec->status = ST_P1_DONE; rec->has_pivot = 0; rec->eval_raw = ldt<GLOBAL>(M); }
                 return;
             }
             phase = 2;
@@ -275,15 +300,15 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
             VI e = einit;
             const double *lrow = M + rstar * stride;
             for (int c = 1 + tid; c < W; c += NT) {
-                const double coef = ldg_cg(lrow + c);
+                const double coef = ldt<GLOBAL>(lrow + c);
                 if (is_unres(T, T.vcol[c]) || coef < -prec) {
-                    const double quo = -ldg_cg(M + c) / coef;
+                    const double quo = -ldt<GLOBAL>(M + c) / coef;
                     if (e.v < quo) { e.v = quo; e.i = c; }
                 }
             }
             e = block_reduce_vi<false>(e, einit, s.red);
             if (e.i == INT_MAX) {  // simplex.ts:73-76
-                if (tid == 0) { rec->status = ST_INFEASIBLE; rec->has_pivot = 0; rec->eval_raw = ldg_cg(M); }
+                if (tid == 0) { rec->status = ST_INFEASIBLE; rec->has_pivot = 0; rec->eval_raw = ldt<GLOBAL>(M); }
                 return;
             }
             cstar = e.i;
@@ -301,14 +326,14 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
                 const int end = min(start + bsz - 1, W - 1);
                 VI x = init;
                 for (int c = start + tid; c <= end; c += NT) {
-                    const double rc = ldg_cg(M + c);
+                    const double rc = ldt<GLOBAL>(M + c);
                     const double v = (rc < 0 && is_unres(T, T.vcol[c])) ? -rc : rc;
                     if (v > x.v) { x.v = v; x.i = c; }
                 }
                 x = block_reduce_vi<false>(x, init, s.red);
                 if (x.i != INT_MAX) cstar = x.i;
             }
-            if (cstar >= 0) isneg = (ldg_cg(M + cstar) < 0 && is_unres(T, T.vcol[cstar])) ? 1 : 0;
+            if (cstar >= 0) isneg = (ldt<GLOBAL>(M + cstar) < 0 && is_unres(T, T.vcol[cstar])) ? 1 : 0;
         } else {
             if (tid == 0) {
                 int c0, n0;
@@ -322,7 +347,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
             __syncthreads();
         }
         if (cstar < 0) {  // optimal (simplex.ts:265-269); setEvaluation rounding is done on the host
-            if (tid == 0) { rec->status = ST_OPTIMAL; rec->phase = 2; rec->has_pivot = 0; rec->eval_raw = ldg_cg(M); }
+            if (tid == 0) { rec->status = ST_OPTIMAL; rec->phase = 2; rec->has_pivot = 0; rec->eval_raw = ldt<GLOBAL>(M); }
             return;
         }
         // ratio test (simplex.ts:271-296) fused with staging of the pivot column
@@ -330,12 +355,12 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
         VI m = init;
         int dmin = INT_MAX;
         for (int r = tid; r < H; r += NT) {
-            const double col = ldg_cg(M + r * stride + cstar);
+            const double col = ldt<GLOBAL>(M + r * stride + cstar);
             T.pcol[r] = col;
             if (nz16(col)) cnt++;
             if (r == 0) continue;
             if (-prec < col && col < prec) continue;
-            const double rhs = ldg_cg(M + r * stride);
+            const double rhs = ldt<GLOBAL>(M + r * stride);
             if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
             const double quo = isneg ? -rhs / col : rhs / col;
             if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
@@ -350,7 +375,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
             if (tid == 0) {
                 rec->status = ST_UNBOUNDED; rec->phase = 2; rec->has_pivot = 0;
                 rec->unbounded_var = T.vcol[cstar];
-                rec->eval_raw = ldg_cg(M);
+                rec->eval_raw = ldt<GLOBAL>(M);
             }
             return;
         }
@@ -359,14 +384,16 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
     if (!col_staged) {
         cnt = 0;
         for (int r = tid; r < H; r += NT) {
-            const double col = ldg_cg(M + r * stride + cstar);
+            const double col = ldt<GLOBAL>(M + r * stride + cstar);
             T.pcol[r] = col;
             if (nz16(col)) cnt++;
         }
         cnt = block_reduce_int<1>(cnt, s.red);
     }
-    cta_stage_pivot(T, rec, phase, rstar, cstar, isneg, cnt);
+    cta_stage_pivot<GLOBAL>(T, rec, phase, rstar, cstar, isneg, cnt);
 }
+
+__device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s);
 
 // Standalone selection (engine 1, the first pivot of every solve, and Tableau.pivot()).
 // force_r/force_c >= 0: stage exactly that pivot (== Tableau.pivot(r, c)).
@@ -383,12 +410,14 @@ __global__ void __launch_bounds__(512) k_select(const TabDev *Tp, Rec *rec, int 
             if (nz16(col)) cnt++;
         }
         cnt = block_reduce_int<1>(cnt, s.red);
-        cta_stage_pivot(T, rec, rec->phase, force_r, force_c, 0, cnt);
+        cta_stage_pivot<true>(T, rec, rec->phase, force_r, force_c, 0, cnt);
         return;
     }
     if (rec->status != ST_RUNNING || rec->has_pivot) return;
     if (rec->stop_at >= 0 && rec->done >= rec->stop_at) return;
-    cta_select(T, rec, s);
+    cta_select<true>(T, rec, s);
+    __syncthreads();
+    if (rec->lookahead && rec->has_pivot && rec->phase == 2 && T.nOpt == 0) cta_price_next(T, rec, s);
 }
 
 // ---- TMA (1-D bulk copy) + mbarrier helpers: raw pivot row HBM/L2 -> shared memory ----------
@@ -434,141 +463,7 @@ __device__ __forceinline__ void st_v2(double *p, double2 v) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
-constexpr int STEP_THREADS = 256;
-constexpr int ROW_CHUNK = 8;
-
-// Shared-memory staging + normalisation of the pivot row (simplex.ts:352-364 and the lazy flush
-// of 380-382): frow[c] = final content of the pivot row after the pivot.
-__device__ __forceinline__ void stage_pivot_row(const TabDev &T, double *frow, uint64_t *bar, uint32_t parity,
-                                                int cstar, double q, int flush) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const uint32_t bytes = (uint32_t)T.stride * 8u;
-    if (tid == 0) {
-        mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(frow, T.prow, bytes, bar);
-    }
-    mbar_wait(bar, parity);
-    for (int c = tid; c < T.stride; c += NT) {
-        const double v = frow[c];
-        double f = nz16(v) ? v / q : 0.0;
-        if (c == cstar) f = 1.0 / q;
-        if (flush && !nz16(f) && f != 0.0) f = 0.0;
-        frow[c] = f;
-    }
-    __syncthreads();
-}
-
-// Rank-1 update of rows [r0, r0+nr) (simplex.ts:367-391), pivot row rewrite, optional rows.
-__device__ __forceinline__ void update_rows(const TabDev &T, const double *frow, int r0, int nr, int rstar,
-                                            int cstar, double q, bool do_opt) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const size_t stride = (size_t)T.stride;
-    const int npair = T.stride >> 1;
-    const double2 *frow2 = reinterpret_cast<const double2 *>(frow);
-    const int cpair = cstar >> 1;
-    for (int rb = r0; rb < r0 + nr; rb += ROW_CHUNK) {
-        double coef[ROW_CHUNK];
-        bool act[ROW_CHUNK];
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < ROW_CHUNK; j++) {
-            const int r = rb + j;
-            const bool valid = (r < r0 + nr) && (r != rstar);
-            coef[j] = valid ? T.pcol[r] : 0.0;
-            act[j] = valid && nz16(coef[j]);
-            any |= act[j];
-            if (valid && !act[j] && coef[j] != 0.0 && tid == 0) T.M[r * stride + cstar] = 0.0;  // simplex.ts:386-388
-        }
-        if (any) {
-            for (int c2 = tid; c2 < npair; c2 += NT) {
-                const double2 f = frow2[c2];
-                const bool z0 = nz16(f.x), z1 = nz16(f.y);
-                const bool pc = (c2 == cpair);
-                if (!z0 && !z1 && !pc) continue;  // zero pivot-row entries touch nothing (nonZeroColumns)
-                double2 old[ROW_CHUNK];
-#pragma unroll
-                for (int j = 0; j < ROW_CHUNK; j++)
-                    if (act[j]) old[j] = ld_v2(T.M + (rb + j) * stride + 2 * c2);
-#pragma unroll
-                for (int j = 0; j < ROW_CHUNK; j++) {
-                    if (!act[j]) continue;
-                    double2 nv = old[j];
-                    if (z0) nv.x = __dsub_rn(old[j].x, __dmul_rn(coef[j], f.x));
-                    if (z1) nv.y = __dsub_rn(old[j].y, __dmul_rn(coef[j], f.y));
-                    if (pc) {
-                        const double pv = -coef[j] / q;  // simplex.ts:385
-                        if (cstar & 1) nv.y = pv; else nv.x = pv;
-                    }
-                    st_v2(T.M + (rb + j) * stride + 2 * c2, nv);
-                }
-            }
-        }
-        if (rstar >= rb && rstar < rb + ROW_CHUNK && rstar < r0 + nr) {
-            double *dst = T.M + rstar * stride;
-            for (int c = tid; c < T.stride; c += NT) dst[c] = frow[c];
-        }
-    }
-    if (do_opt) {  // simplex.ts:393-412 (exact-zero predicates)
-        for (int o = 0; o < T.nOpt; o++) {
-            const double coefficient = T.optcoef[o];
-            if (coefficient == 0.0) continue;
-            double *rc = T.opt + (size_t)o * stride;
-            for (int c = tid; c < T.W; c += NT) {
-                const double v0 = frow[c];
-                double v = rc[c];
-                bool wr = false;
-                if (v0 != 0.0) { v = __dsub_rn(v, __dmul_rn(coefficient, v0)); wr = true; }
-                if (c == cstar) { v = -coefficient / q; wr = true; }
-                if (wr) rc[c] = v;
-            }
-        }
-    }
-}
-
-// One launch == one simplex iteration.  do_select: the last CTA selects the next pivot.
-__global__ void __launch_bounds__(STEP_THREADS, 2) k_pivot_step(const TabDev *Tp, Rec *rec, int do_select) {
-    extern __shared__ __align__(128) double frow[];
-    __shared__ TabDev T;
-    __shared__ SelSmem sel;
-    __shared__ uint64_t bar;
-    __shared__ int s_last;
-    const int tid = threadIdx.x;
-    if (rec->status != ST_RUNNING || !rec->has_pivot) return;
-    if (rec->stop_at >= 0 && rec->done >= rec->stop_at) return;
-    if (tid == 0) {
-        T = *Tp;
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const int rstar = rec->r, cstar = rec->c, flush = rec->flush;
-    const double q = rec->q;
-    stage_pivot_row(T, frow, &bar, 0, cstar, q, flush);
-
-    const int G = gridDim.x, b = blockIdx.x;
-    const int base = T.H / G, rem = T.H % G;
-    const int r0 = b * base + min(b, rem);
-    const int nr = base + (b < rem ? 1 : 0);
-    update_rows(T, frow, r0, nr, rstar, cstar, q, b == G - 1);
-
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int t = atomicAdd(&rec->ticket, 1u);
-        s_last = (t == (unsigned int)(G - 1));
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid == 0) {
-        rec->ticket = 0;
-        rec->done += 1;
-        if (rec->phase == 1) rec->p1 += 1; else rec->p2 += 1;
-        rec->has_pivot = 0;
-    }
-    __syncthreads();
-    if (do_select && !(rec->stop_at >= 0 && rec->done >= rec->stop_at)) cta_select(T, rec, sel);
-}
+#include "jslp_step.cuh"
 
 // Start of every enqueued batch: empty the per-batch pivot log.
 __global__ void k_batch_begin(Rec *rec) {
@@ -613,9 +508,7 @@ __global__ void __launch_bounds__(256) k_add_cuts(const TabDev *Tp, const CutDev
 }
 
 // isIntegral + getMostFractionalVar (mip-utils.ts:43-61,100-126) over the RHS column.
-__global__ void __launch_bounds__(256) k_mip_scan(const TabDev *Tp, MipOut *out) {
-    __shared__ RedSmem red;
-    const TabDev &T = *Tp;
+__device__ __forceinline__ void cta_mip_scan(const TabDev &T, MipOut *out, RedSmem &red) {
     const VI init = {0.0, INT_MAX};
     VI best = init;  // (fraction, position in model.integerVariables)
     int nonint = 0;
@@ -627,7 +520,7 @@ __global__ void __launch_bounds__(256) k_mip_scan(const TabDev *Tp, MipOut *out)
         const double x = T.M[(size_t)r * T.stride];
         const double fr = fabs(x - js_round(x));
         if (fr > T.prec) nonint = 1;
-        if (fr > best.v || (fr == best.v && fr > 0.0 && p < best.i)) { best.v = fr; best.i = p; }
+        if (fr > 0.0 && (fr > best.v || (fr == best.v && p < best.i))) { best.v = fr; best.i = p; }
     }
     best = block_reduce_vi<false>(best, init, red);
     nonint = block_reduce_int<1>(nonint, red);
@@ -642,6 +535,15 @@ __global__ void __launch_bounds__(256) k_mip_scan(const TabDev *Tp, MipOut *out)
             }
         }
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_mip_scan(const TabDev *Tp, MipOut *out) {
+    __shared__ RedSmem red;
+    __shared__ TabDev T;
+    if (threadIdx.x == 0) T = *Tp;
+    __syncthreads();
+    cta_mip_scan(T, out, red);
 }
 
 // Layout conversion between the reference's stride == width matrix and the padded device rows.

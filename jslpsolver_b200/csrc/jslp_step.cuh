@@ -1,0 +1,347 @@
+// jslpsolver_b200/csrc/jslp_step.cuh -- the fused pivot step (included by jslp_kernels.cuh).
+//
+// One launch == one simplex iteration on a tableau that lives in HBM / L2:
+//   head   TMA (cp.async.bulk + mbarrier) stages the raw pivot row into shared memory; every CTA
+//          normalises it there (simplex.ts:352-364, lazy flush 380-382)
+//   body   each CTA streams its block of rows with 128-bit loads/stores:
+//          M[r][c] = M[r][c] - coef_r * prow[c]   (two roundings, simplex.ts:379), pivot column
+//          entry -coef_r / q (385), pivot row rewrite, optional-objective rows (393-412)
+//   look-ahead (phase 2)  the entering column of the NEXT pivot was priced one step ahead (it only
+//          needs the updated cost row, which is known as soon as this pivot is chosen), so each CTA
+//          runs the ratio test (271-296) on its own freshly written rows and publishes a 40-byte
+//          partial; it also stages the next pivot column
+//   tail   the last CTA (atomic ticket) reduces the partials to the leaving row, stages the pivot
+//          (raw row copy, label swap, log) and prices the pivot after that one.  When look-ahead
+//          does not apply (phase 1, optional objectives, bootstrap) it runs the generic selection.
+#pragma once
+// (included inside namespace jslp)
+
+// ---- pricing of the pivot AFTER the staged one (phase 2, no optional objectives) -------------
+// cost'[c] is the cost row as the staged pivot will leave it; the expression must be the very one
+// update_rows evaluates for row 0, so that the decision is bit-identical to pricing afterwards.
+__device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int W = T.W, cstar = rec->c;
+    const double q = rec->q, prec = T.prec;
+    const double coef0 = ldg_cg(T.M + cstar);
+    const bool nzc = nz16(coef0);
+    const int nColumns = W - 1;
+    const int bsz = T.use_partial ? T.batch_size : nColumns;
+    const int nb = T.use_partial ? (nColumns + bsz - 1) / bsz : 1;
+    const VI init = {prec, INT_MAX};
+    int found = -1, neg = 0;
+    for (int b = 0; b < nb && found < 0; b++) {
+        const int start = 1 + b * bsz;
+        const int end = min(start + bsz - 1, W - 1);
+        VI x = init;
+        for (int c = start + tid; c <= end; c += NT) {
+            const double cost = ldg_cg(T.M + c);
+            double nc;
+            if (nzc) {
+                if (c == cstar) nc = -coef0 / q;
+                else {
+                    const double v = ldg_cg(T.prow + c);
+                    const double f = nz16(v) ? v / q : 0.0;
+                    nc = nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
+                }
+            } else {
+                nc = (coef0 != 0.0 && c == cstar) ? 0.0 : cost;
+            }
+            const double v2 = (nc < 0 && is_unres(T, T.vcol[c])) ? -nc : nc;
+            if (v2 > x.v) { x.v = v2; x.i = c; }
+        }
+        x = block_reduce_vi<false>(x, init, s.red);
+        if (x.i != INT_MAX) found = x.i;
+    }
+    if (found > 0) {  // isReducedCostNegative of the winner: recompute its updated cost
+        const int c = found;
+        const double cost = ldg_cg(T.M + c);
+        double nc;
+        if (nzc) {
+            if (c == cstar) nc = -coef0 / q;
+            else {
+                const double v = ldg_cg(T.prow + c);
+                const double f = nz16(v) ? v / q : 0.0;
+                nc = nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
+            }
+        } else {
+            nc = (coef0 != 0.0 && c == cstar) ? 0.0 : cost;
+        }
+        neg = (nc < 0 && is_unres(T, T.vcol[c])) ? 1 : 0;
+    }
+    if (tid == 0) { rec->next_c = found > 0 ? found : 0; rec->next_neg = neg; }
+}
+
+// ---- head: TMA staging + normalisation of the pivot row ---------------------------------------
+__device__ __forceinline__ void stage_pivot_row(const TabDev &T, double *frow, uint64_t *bar, uint32_t parity,
+                                                int cstar, double q, int flush) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t bytes = (uint32_t)T.stride * 8u;
+    if (tid == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(frow, T.prow, bytes, bar);
+    }
+    mbar_wait(bar, parity);
+    for (int c = tid; c < T.stride; c += NT) {
+        const double v = frow[c];
+        double f = nz16(v) ? v / q : 0.0;
+        if (c == cstar) f = 1.0 / q;
+        if (flush && !nz16(f) && f != 0.0) f = 0.0;
+        frow[c] = f;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double2 upd2(double2 old, double2 f, bool z0, bool z1, double coef, bool pc, int codd,
+                                        double q) {
+    double2 nv = old;
+    if (z0) nv.x = __dsub_rn(old.x, __dmul_rn(coef, f.x));
+    if (z1) nv.y = __dsub_rn(old.y, __dmul_rn(coef, f.y));
+    if (pc) {
+        const double pv = -coef / q;  // simplex.ts:385
+        if (codd) nv.y = pv; else nv.x = pv;
+    }
+    return nv;
+}
+
+// ---- body: rank-1 update of rows [r0, r0+nr) ---------------------------------------------------
+// RC rows are processed together (RC independent 128-bit loads in flight per thread); PF adds a
+// software prefetch of the next column pair's RC loads before the current pair is stored.
+template <int RC, bool PF>
+__device__ __forceinline__ void update_rows(const TabDev &T, const double *frow, int r0, int nr, int rstar,
+                                            int cstar, double q, bool do_opt) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const size_t stride = (size_t)T.stride;
+    const int npair = T.stride >> 1;
+    double *const Mb = T.M;
+    const double *const pcol = T.pcol;
+    const double2 *frow2 = reinterpret_cast<const double2 *>(frow);
+    const int cpair = cstar >> 1, codd = cstar & 1;
+    for (int rb = r0; rb < r0 + nr; rb += RC) {
+        double coef[RC];
+        bool act[RC];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < RC; j++) {
+            const int r = rb + j;
+            const bool valid = (r < r0 + nr) && (r != rstar);
+            coef[j] = valid ? pcol[r] : 0.0;
+            act[j] = valid && nz16(coef[j]);
+            any |= act[j];
+            if (valid && !act[j] && coef[j] != 0.0 && tid == 0) Mb[r * stride + cstar] = 0.0;  // simplex.ts:386-388
+        }
+        double *const base = Mb + (size_t)rb * stride;
+        if (any && !PF) {
+            for (int c2 = tid; c2 < npair; c2 += NT) {
+                const double2 f = frow2[c2];
+                const bool z0 = nz16(f.x), z1 = nz16(f.y);
+                const bool pc = (c2 == cpair);
+                if (!z0 && !z1 && !pc) continue;  // zero pivot-row entries touch nothing (nonZeroColumns)
+                double2 old[RC];
+#pragma unroll
+                for (int j = 0; j < RC; j++)
+                    if (act[j]) old[j] = ld_v2(base + j * stride + 2 * c2);
+#pragma unroll
+                for (int j = 0; j < RC; j++)
+                    if (act[j]) st_v2(base + j * stride + 2 * c2, upd2(old[j], f, z0, z1, coef[j], pc, codd, q));
+            }
+        } else if (any) {
+            int c2 = tid;
+            double2 f = make_double2(0.0, 0.0), old[RC];
+            if (c2 < npair) {
+                f = frow2[c2];
+#pragma unroll
+                for (int j = 0; j < RC; j++)
+                    if (act[j]) old[j] = ld_v2(base + j * stride + 2 * c2);
+            }
+            while (c2 < npair) {
+                const int n2 = c2 + NT;
+                double2 fn = make_double2(0.0, 0.0), oldn[RC];
+                if (n2 < npair) {
+                    fn = frow2[n2];
+#pragma unroll
+                    for (int j = 0; j < RC; j++)
+                        if (act[j]) oldn[j] = ld_v2(base + j * stride + 2 * n2);
+                }
+                const bool z0 = nz16(f.x), z1 = nz16(f.y);
+                const bool pc = (c2 == cpair);
+                if (z0 || z1 || pc) {
+#pragma unroll
+                    for (int j = 0; j < RC; j++)
+                        if (act[j]) st_v2(base + j * stride + 2 * c2, upd2(old[j], f, z0, z1, coef[j], pc, codd, q));
+                }
+                c2 = n2;
+                f = fn;
+#pragma unroll
+                for (int j = 0; j < RC; j++) old[j] = oldn[j];
+            }
+        }
+        if (rstar >= rb && rstar < rb + RC && rstar < r0 + nr) {
+            double *dst = Mb + rstar * stride;
+            for (int c = tid; c < T.stride; c += NT) dst[c] = frow[c];
+        }
+    }
+    if (do_opt) {  // simplex.ts:393-412 (exact-zero predicates)
+        for (int o = 0; o < T.nOpt; o++) {
+            const double coefficient = T.optcoef[o];
+            if (coefficient == 0.0) continue;
+            double *rc = T.opt + (size_t)o * stride;
+            for (int c = tid; c < T.W; c += NT) {
+                const double v0 = frow[c];
+                double v = rc[c];
+                bool wr = false;
+                if (v0 != 0.0) { v = __dsub_rn(v, __dmul_rn(coefficient, v0)); wr = true; }
+                if (c == cstar) { v = -coefficient / q; wr = true; }
+                if (wr) rc[c] = v;
+            }
+        }
+    }
+}
+
+// ---- look-ahead: ratio-test partial of this CTA's rows against the next entering column ---------
+__device__ __forceinline__ void cta_ratio_partial(const TabDev &T, SelSmem &s, int r0, int nr, int cn, int isneg) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const size_t stride = (size_t)T.stride;
+    const double prec = T.prec;
+    const VI init = {INFINITY, INT_MAX};
+    VI m = init;
+    int dmin = INT_MAX, cnt = 0;
+    for (int r = r0 + tid; r < r0 + nr; r += NT) {
+        const double col = ldg_cg(T.M + r * stride + cn);
+        T.pcol[r] = col;  // pivot column of the next pivot (this CTA is the only reader of these entries)
+        if (nz16(col)) cnt++;
+        if (r == 0) continue;
+        if (-prec < col && col < prec) continue;
+        const double rhs = ldg_cg(T.M + r * stride);
+        if (col > 0 && prec > rhs && rhs > -prec) {
+            if (r < dmin) dmin = r;
+            continue;
+        }
+        const double quo = isneg ? -rhs / col : rhs / col;
+        if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+    }
+    const int dall = block_reduce_int<0>(dmin, s.red);
+    const VI mall = block_reduce_vi<true>(m, init, s.red);
+    cnt = block_reduce_int<1>(cnt, s.red);
+    Part *p = T.part + blockIdx.x;
+    if (tid == 0) { p->minq = mall.v; p->minr = mall.i; p->dmin = dall; p->cnt = cnt; }
+}
+
+// ---- tail (look-ahead): reduce the partials, stage the next pivot, price the one after it -------
+__device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int cn = rec->next_c, isneg = rec->next_neg;
+    if (cn == 0) {  // nothing prices in: optimal (simplex.ts:265-269); setEvaluation is done on the host
+        if (tid == 0) { rec->status = ST_OPTIMAL; rec->phase = 2; rec->has_pivot = 0; rec->eval_raw = ldg_cg(T.M); }
+        return;
+    }
+    const VI init = {INFINITY, INT_MAX};
+    VI m = init;
+    int dmin = INT_MAX, cnt = 0;
+    const volatile Part *parts = T.part;
+    for (int b = tid; b < G; b += NT) {
+        const double pq = parts[b].minq;
+        const int pr = parts[b].minr, pd = parts[b].dmin;
+        cnt += parts[b].cnt;
+        if (pd < dmin) dmin = pd;
+        if (pr != INT_MAX && (pq < m.v || (pq == m.v && pr < m.i))) { m.v = pq; m.i = pr; }
+    }
+    const int dall = block_reduce_int<0>(dmin, s.red);
+    const VI mall = block_reduce_vi<true>(m, init, s.red);
+    cnt = block_reduce_int<1>(cnt, s.red);
+    int rstar;
+    if (dall != INT_MAX) rstar = dall;
+    else if (mall.i != INT_MAX) rstar = mall.i;
+    else {  // unbounded (simplex.ts:298-303)
+        if (tid == 0) {
+            rec->status = ST_UNBOUNDED; rec->phase = 2; rec->has_pivot = 0;
+            rec->unbounded_var = T.vcol[cn];
+            rec->eval_raw = ldg_cg(T.M);
+        }
+        return;
+    }
+    cta_stage_pivot<true>(T, rec, 2, rstar, cn, isneg, cnt);
+    __syncthreads();
+    cta_price_next(T, rec, s);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+// do_select: 0 = update only (two-kernel engine), 1 = the last CTA selects the next pivot.
+template <int NTHREADS, int MINB, int RC, bool PF>
+__global__ void __launch_bounds__(NTHREADS, MINB) k_pivot_step(const TabDev *Tp, Rec *rec, int do_select) {
+    extern __shared__ __align__(128) double frow[];
+    __shared__ TabDev T;
+    __shared__ SelSmem sel;
+    __shared__ uint64_t bar;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    if (rec->status != ST_RUNNING || !rec->has_pivot) return;
+    if (rec->stop_at >= 0 && rec->done >= rec->stop_at) return;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, g0 = 0;
+    if (tid == 0) {
+        T = *Tp;
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const bool dbg = T.dbg != nullptr && rec->done < T.dbg_cap;
+    if (dbg && tid == 0) {
+        t0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    }
+    const int rstar = rec->r, cstar = rec->c, flush = rec->flush;
+    const int launch = rec->done;
+    const double q = rec->q;
+    const int next_c = rec->next_c, next_neg = rec->next_neg;
+    const bool stop_after = rec->stop_at >= 0 && rec->done + 1 >= rec->stop_at;
+    stage_pivot_row(T, frow, &bar, 0, cstar, q, flush);
+    if (dbg && tid == 0) t1 = clock64();
+
+    const int G = gridDim.x, b = blockIdx.x;
+    const int base = T.H / G, rem = T.H % G;
+    const int r0 = b * base + min(b, rem);
+    const int nr = base + (b < rem ? 1 : 0);
+    update_rows<RC, PF>(T, frow, r0, nr, rstar, cstar, q, b == G - 1);
+    if (dbg && tid == 0) t2 = clock64();
+
+    const bool fast = do_select && next_c >= 0 && !stop_after;
+    if (fast && next_c > 0) {
+        __syncthreads();  // this CTA's rows are written: read them back for the look-ahead ratio test
+        cta_ratio_partial(T, sel, r0, nr, next_c, next_neg);
+    }
+    __threadfence();
+    __syncthreads();
+    if (dbg && tid == 0) t3 = clock64();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(&rec->ticket, 1u);
+        s_last = (t == (unsigned int)(G - 1));
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid == 0) {
+            rec->ticket = 0;
+            rec->done += 1;
+            if (rec->phase == 1) rec->p1 += 1; else rec->p2 += 1;
+            rec->has_pivot = 0;
+        }
+        __syncthreads();
+        if (do_select && !stop_after) {
+            if (fast) {
+                cta_tail_lookahead(T, rec, sel, G);
+            } else {
+                cta_select<true>(T, rec, sel);
+                __syncthreads();
+                if (rec->lookahead && rec->has_pivot && rec->phase == 2 && T.nOpt == 0) cta_price_next(T, rec, sel);
+            }
+        }
+    }
+    if (dbg && tid == 0) {
+        t4 = clock64();
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *d = T.dbg + ((size_t)launch * T.dbg_grid + b) * 8;
+        d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = s_last; d[7] = nr;
+    }
+}
+

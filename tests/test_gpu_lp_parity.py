@@ -11,7 +11,10 @@ from helpers import compare_solutions, strip_timeouts
 pytestmark = pytest.mark.gpu
 BUNDLE = load_bundle()
 ASSIGNMENT_UNCONFIRMED = {"StockCuttingProblem.json", "Vendor Selection.json"}
-ENGINES = {"two_kernel": 1, "fused": 2}
+# engine, or (engine, look-ahead tail on/off, fused-step kernel variant)
+ENGINES = {"two_kernel": 1, "fused": 2, "resident": 4, "fused_generic_tail": (2, 0, 0),
+           "fused_v1_prefetch": (2, 1, 1), "fused_v2_occ4": (2, 1, 2), "fused_v3_t512": (2, 1, 3),
+           "fused_v5_t128": (2, 1, 5)}
 
 
 def same_bits(a, b):
@@ -32,12 +35,20 @@ def oracle_lp(it, precision=1e-8, check_cycles=True, log=1 << 16):
 
 
 def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
+    """engine: JSLP_OPT_ENGINE value, or a tuple (engine, lookahead, step variant)."""
     from jslpsolver_b200 import _lib
     from jslpsolver_b200.tableau import GpuTableau
+    lookahead = variant = None
+    if isinstance(engine, tuple):
+        engine, lookahead, variant = engine
     g = GpuTableau(precision)
     g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, it.unrestricted, it.integerIndices, it.optionalCosts)
     g.set_option(_lib.OPT_ENGINE, engine)
     g.set_option(_lib.OPT_PIVOT_LOG_CAP, log)
+    if lookahead is not None:
+        g.set_option(_lib.OPT_LOOKAHEAD, lookahead)
+    if variant is not None:
+        g.set_option(_lib.OPT_STEP_VARIANT, variant)
     if batch:
         g.set_option(_lib.OPT_BATCH, batch)
     return g
@@ -227,17 +238,28 @@ def test_row_capacity_growth():
 
 
 # ------------------------------------------------------------------ branch and cut
+# (engine, speculation width): HBM path one node at a time (the reference's literal order), then
+# speculative rounds with shared-memory-resident node batches
+BNB_MODES = {"hbm_seq": (2, 1), "auto_seq": (0, 1), "auto_spec8": (0, 8), "auto_spec32": (0, 32), "hbm_spec4": (2, 4)}
+
+
+@pytest.mark.parametrize("mode", list(BNB_MODES))
 @pytest.mark.parametrize("fx", [f for f in BUNDLE["fixtures"] if (f["model"].get("ints") or f["model"].get("binaries"))
                                 and f["file"] != "Vendor Selection.json"], ids=lambda f: f["file"])
-def test_mip_fixture_node_sequence(fx):
-    """Same pop order, same per-node outcomes, same final tableau as the reference's loop."""
+def test_mip_fixture_node_sequence(fx, mode):
+    """Same pop order, same per-node outcomes, same final tableau as the reference's loop --
+    whatever the speculation width or evaluation back-end."""
     import jslpsolver_b200 as J
     from oracle import ref_model
+    if fx["file"] == "Monster_II.json" and mode not in ("hbm_seq", "auto_spec8"):
+        pytest.skip("large MIP: covered by two modes")
     jm = strip_timeouts(fx["model"])
     osol = ref_model.solve_full(jm, fast_cycles=True, node_log=1 << 20)
     if osol.tableau is None:
         pytest.skip("decided by presolve")
-    gsol = J.Solve(jm, full=True)
+    s = J.Solver()
+    s.engine, s.max_spec_batch = BNB_MODES[mode]
+    gsol = s.Solve(jm, full=True)
     gt = gsol._tableau
     onl, gnl = osol.tableau.node_log(), gt.node_log()
     assert gnl.shape == onl.shape, (gnl.shape, onl.shape)
