@@ -119,7 +119,7 @@ struct jslp_tab {
     int isIntegralFlag = 0, bncIterations = 0;
     // options
     int engine = 0, batch = 256;
-    int variant = 0, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1;
+    int variant = 0, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0;
     int64_t host_log_cap = 0;
     std::vector<int4> host_log;
     // graphs
@@ -363,6 +363,9 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
         case JSLP_OPT_LOOKAHEAD:
             t->lookahead = value != 0;
             return JSLP_OK;
+        case JSLP_OPT_PDL:
+            t->pdl = value != 0;
+            return JSLP_OK;
         case JSLP_OPT_TIMELINE:
             if (value < 0 || value > 4096) return fail(JSLP_E_INVALID, "timeline launches must be 0..4096");
             t->timeline_cap = (int)value;
@@ -388,7 +391,7 @@ extern "C" int jslp_debug_timeline(jslp_tab *t, int64_t *out, int64_t cap_values
 
 // ---------------------------------------------------------------------------------------------
 // Instantiations of the fused step: <threads, min CTAs/SM, rows per pass, software prefetch>.
-typedef void (*step_fn_t)(const TabDev *, Rec *, int);
+typedef void (*step_fn_t)(const TabDev *, Rec *, int, const double *, int);
 struct StepVariant {
     step_fn_t fn;
     int threads, ctas_per_sm;
@@ -441,7 +444,8 @@ static int build_graphs(jslp_tab *t) {
     const int smem = t->stride * 8;
     int rc = ensure_step_bufs(t, grid);
     if (rc) return rc;
-    if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem && t->g_variant == t->variant)
+    if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem &&
+        t->g_variant == t->variant + 100 * t->pdl)
         return JSLP_OK;
     drop_graphs(t);
     cudaStream_t s = t->ctx->stream;
@@ -453,11 +457,34 @@ static int build_graphs(jslp_tab *t) {
         k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
         if (mode == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
             k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-            for (int i = 0; i < t->batch; i++) sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 1);
+            for (int i = 0; i < t->batch; i++) {
+                if (t->pdl && i > 0) {
+                    // programmatic dependent launch: step i's CTAs are scheduled while step i-1
+                    // drains and block in griddepcontrol.wait until it has completed
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof(cfg));
+                    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sv.threads);
+                    cfg.dynamicSmemBytes = smem; cfg.stream = s;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    const TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = 1; const double *a3 = t->hd.prow; int a4 = t->stride;
+                    void *args[] = {&a0, &a1, &a2, &a3, &a4};
+                    cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args);
+                    if (le != cudaSuccess) {
+                        cudaGraph_t junk;
+                        cudaStreamEndCapture(s, &junk);
+                        return fail(JSLP_E_CUDA, std::string("PDL launch: ") + cudaGetErrorString(le));
+                    }
+                } else {
+                    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 1, t->hd.prow, t->stride);
+                }
+            }
         } else {  // two kernels per pivot
             for (int i = 0; i < t->batch; i++) {
                 k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-                sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0);
+                sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0, t->hd.prow, t->stride);
             }
         }
         cudaError_t e = cudaStreamEndCapture(s, &g);
@@ -468,7 +495,7 @@ static int build_graphs(jslp_tab *t) {
         if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
         if (mode == 0) t->g_fused = ge; else t->g_simple = ge;
     }
-    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant;
+    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * t->pdl;
     return JSLP_OK;
 }
 
@@ -789,7 +816,7 @@ extern "C" int jslp_pivot(jslp_tab *t, int row, int col) {
     *t->h_rec = init;
     CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
     k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, row, col);
-    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0);
+    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0, t->hd.prow, t->stride);
     ctx->launches += 2;
     CK(cudaGetLastError());
     if (t->host_log_cap > 0) {  // explicit pivots are part of the executed-pivot log

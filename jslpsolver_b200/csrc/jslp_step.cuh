@@ -17,79 +17,66 @@
 // (included inside namespace jslp)
 
 // ---- pricing of the pivot AFTER the staged one (phase 2, no optional objectives) -------------
-// cost'[c] is the cost row as the staged pivot will leave it; the expression must be the very one
-// update_rows evaluates for row 0, so that the decision is bit-identical to pricing afterwards.
-__device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
+// cost'[c] is the cost row as the staged pivot (rstar, cstar, q) will leave it; the expression must
+// be the very one update_rows evaluates for row 0, so the decision is bit-identical to pricing
+// afterwards.  rowsrc = raw pivot row (the prow side buffer or the tableau row itself).  All loads
+// of the first batch are issued before anything is consumed: one L2 round trip.
+// new_label = variable that labels column cstar after the pivot's swap (simplex.ts:339-343).
+__device__ __forceinline__ double priced_cost(double cost, double v, double coef0, bool nzc, bool is_pc, double q) {
+    if (nzc) {
+        if (is_pc) return -coef0 / q;
+        const double f = nz16(v) ? v / q : 0.0;
+        return nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
+    }
+    return (coef0 != 0.0 && is_pc) ? 0.0 : cost;
+}
+
+__device__ void cta_price_core(const TabDev &T, SelSmem &s, const double *rowsrc, double q, double coef0, int cstar,
+                               int new_label, int *found_out, int *neg_out) {
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int W = T.W, cstar = rec->c;
-    const double q = rec->q, prec = T.prec;
-    const double coef0 = ldg_cg(T.M + cstar);
+    const int W = T.W;
+    const double prec = T.prec;
     const bool nzc = nz16(coef0);
     const int nColumns = W - 1;
     const int bsz = T.use_partial ? T.batch_size : nColumns;
     const int nb = T.use_partial ? (nColumns + bsz - 1) / bsz : 1;
     const VI init = {prec, INT_MAX};
-    int found = -1, neg = 0;
+    int found = -1;
     for (int b = 0; b < nb && found < 0; b++) {
         const int start = 1 + b * bsz;
         const int end = min(start + bsz - 1, W - 1);
         VI x = init;
+        int myneg = 0;
         for (int c = start + tid; c <= end; c += NT) {
             const double cost = ldg_cg(T.M + c);
-            double nc;
-            if (nzc) {
-                if (c == cstar) nc = -coef0 / q;
-                else {
-                    const double v = ldg_cg(T.prow + c);
-                    const double f = nz16(v) ? v / q : 0.0;
-                    nc = nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
-                }
-            } else {
-                nc = (coef0 != 0.0 && c == cstar) ? 0.0 : cost;
-            }
-            const double v2 = (nc < 0 && is_unres(T, T.vcol[c])) ? -nc : nc;
-            if (v2 > x.v) { x.v = v2; x.i = c; }
+            const double v = ldg_cg(rowsrc + c);
+            const double nc = priced_cost(cost, v, coef0, nzc, c == cstar, q);
+            bool un = false;
+            if (T.unres != nullptr && nc < 0) un = is_unres(T, c == cstar ? new_label : T.vcol[c]);
+            const double v2 = un ? -nc : nc;
+            if (v2 > x.v) { x.v = v2; x.i = c; myneg = un ? 1 : 0; }
         }
+        const int mine = x.i;
         x = block_reduce_vi<false>(x, init, s.red);
-        if (x.i != INT_MAX) found = x.i;
-    }
-    if (found > 0) {  // isReducedCostNegative of the winner: recompute its updated cost
-        const int c = found;
-        const double cost = ldg_cg(T.M + c);
-        double nc;
-        if (nzc) {
-            if (c == cstar) nc = -coef0 / q;
-            else {
-                const double v = ldg_cg(T.prow + c);
-                const double f = nz16(v) ? v / q : 0.0;
-                nc = nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
-            }
-        } else {
-            nc = (coef0 != 0.0 && c == cstar) ? 0.0 : cost;
+        if (x.i != INT_MAX) {
+            found = x.i;
+            if (mine == x.i) s.bc_neg = myneg;  // exactly one thread owns the winning column
         }
-        neg = (nc < 0 && is_unres(T, T.vcol[c])) ? 1 : 0;
-    }
-    if (tid == 0) { rec->next_c = found > 0 ? found : 0; rec->next_neg = neg; }
-}
-
-// ---- head: TMA staging + normalisation of the pivot row ---------------------------------------
-__device__ __forceinline__ void stage_pivot_row(const TabDev &T, double *frow, uint64_t *bar, uint32_t parity,
-                                                int cstar, double q, int flush) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const uint32_t bytes = (uint32_t)T.stride * 8u;
-    if (tid == 0) {
-        mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(frow, T.prow, bytes, bar);
-    }
-    mbar_wait(bar, parity);
-    for (int c = tid; c < T.stride; c += NT) {
-        const double v = frow[c];
-        double f = nz16(v) ? v / q : 0.0;
-        if (c == cstar) f = 1.0 / q;
-        if (flush && !nz16(f) && f != 0.0) f = 0.0;
-        frow[c] = f;
     }
     __syncthreads();
+    *found_out = found > 0 ? found : 0;
+    *neg_out = found > 0 ? s.bc_neg : 0;
+    __syncthreads();
+}
+
+// Generic entry: the pivot is already staged (prow side buffer, labels swapped, rec filled).
+__device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
+    const int cstar = rec->c;
+    const double q = rec->q;
+    const double coef0 = ldg_cg(T.M + cstar);
+    int found, neg;
+    cta_price_core(T, s, T.prow, q, coef0, cstar, T.vcol[cstar], &found, &neg);
+    if (threadIdx.x == 0) { rec->next_c = found; rec->next_neg = neg; }
 }
 
 __device__ __forceinline__ double2 upd2(double2 old, double2 f, bool z0, bool z1, double coef, bool pc, int codd,
@@ -198,39 +185,52 @@ __device__ __forceinline__ void update_rows(const TabDev &T, const double *frow,
     }
 }
 
+
+// Entry (r, c) of the tableau as the pivot (rstar, cstar, q) leaves it, from its old value: the
+// single-element form of update_rows (simplex.ts:352-391), used to run the look-ahead ratio test on
+// values that were loaded while the pivot row was still being staged.
+__device__ __forceinline__ double new_entry(double old, bool is_prow, double coef, double f, bool is_pc, double q) {
+    if (is_prow) return f;
+    if (nz16(coef)) {
+        if (is_pc) return -coef / q;
+        return nz16(f) ? __dsub_rn(old, __dmul_rn(coef, f)) : old;
+    }
+    return (coef != 0.0 && is_pc) ? 0.0 : old;
+}
+
 // ---- look-ahead: ratio-test partial of this CTA's rows against the next entering column ---------
-__device__ __forceinline__ void cta_ratio_partial(const TabDev &T, SelSmem &s, int r0, int nr, int cn, int isneg) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const size_t stride = (size_t)T.stride;
+// One row per thread (nr <= blockDim.x); col/rhs are the UPDATED entries of that row.
+__device__ __forceinline__ void cta_ratio_partial(const TabDev &T, SelSmem &s, int r0, int nr, bool have, double col,
+                                                  double rhs, int isneg) {
+    const int tid = threadIdx.x;
     const double prec = T.prec;
     const VI init = {INFINITY, INT_MAX};
     VI m = init;
     int dmin = INT_MAX, cnt = 0;
-    for (int r = r0 + tid; r < r0 + nr; r += NT) {
-        const double col = ldg_cg(T.M + r * stride + cn);
+    if (have) {
+        const int r = r0 + tid;
         T.pcol[r] = col;  // pivot column of the next pivot (this CTA is the only reader of these entries)
-        if (nz16(col)) cnt++;
-        if (r == 0) continue;
-        if (-prec < col && col < prec) continue;
-        const double rhs = ldg_cg(T.M + r * stride);
-        if (col > 0 && prec > rhs && rhs > -prec) {
-            if (r < dmin) dmin = r;
-            continue;
+        if (nz16(col)) cnt = 1;
+        if (r != 0 && !(-prec < col && col < prec)) {
+            if (col > 0 && prec > rhs && rhs > -prec) dmin = r;
+            else {
+                const double quo = isneg ? -rhs / col : rhs / col;
+                if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+            }
         }
-        const double quo = isneg ? -rhs / col : rhs / col;
-        if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
     }
     const int dall = block_reduce_int<0>(dmin, s.red);
     const VI mall = block_reduce_vi<true>(m, init, s.red);
     cnt = block_reduce_int<1>(cnt, s.red);
     Part *p = T.part + blockIdx.x;
     if (tid == 0) { p->minq = mall.v; p->minr = mall.i; p->dmin = dall; p->cnt = cnt; }
+    (void)nr;
 }
 
 // ---- tail (look-ahead): reduce the partials, stage the next pivot, price the one after it -------
-__device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G) {
+// Two dependent L2 round trips: (1) the partials, (2) everything that depends on the leaving row.
+__device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G, int cn, int isneg, int log_n) {
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int cn = rec->next_c, isneg = rec->next_neg;
     if (cn == 0) {  // nothing prices in: optimal (simplex.ts:265-269); setEvaluation is done on the host
         if (tid == 0) { rec->status = ST_OPTIMAL; rec->phase = 2; rec->has_pivot = 0; rec->eval_raw = ldg_cg(T.M); }
         return;
@@ -260,54 +260,101 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G)
         }
         return;
     }
-    cta_stage_pivot<true>(T, rec, 2, rstar, cn, isneg, cnt);
-    __syncthreads();
-    cta_price_next(T, rec, s);
+    // round trip 2: pivot element, cost-row entry, labels, raw pivot row, first pricing batch
+    const double *rowp = T.M + (size_t)rstar * T.stride;
+    const double q = ldg_cg(rowp + cn);
+    const double coef0 = ldg_cg(T.M + cn);
+    const int leaving = T.vrow[rstar];
+    const int entering = T.vcol[cn];
+    for (int c = tid; c < T.stride; c += NT) T.prow[c] = c < T.W ? ldg_cg(rowp + c) : 0.0;
+    int found, neg;
+    cta_price_core(T, s, rowp, q, coef0, cn, leaving, &found, &neg);
+    if (tid == 0) {
+        if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rstar | (1 << 30), cn, leaving, entering);
+        rec->log_n = log_n + 1;
+        T.vrow[rstar] = entering;  // simplex.ts:339-349
+        T.vcol[cn] = leaving;
+        rec->phase = 2; rec->r = rstar; rec->c = cn; rec->q = q; rec->is_neg = isneg;
+        rec->flush = (cnt - (nz16(q) ? 1 : 0)) > 0;
+        rec->has_pivot = 1;
+        rec->next_c = found; rec->next_neg = neg;
+    }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
 // do_select: 0 = update only (two-kernel engine), 1 = the last CTA selects the next pivot.
+// prow_arg / stride_arg duplicate TabDev.prow / stride (both immutable after jslp_tab_create) so the
+// TMA copy of the pivot row can be issued before the descriptor has been fetched.
 template <int NTHREADS, int MINB, int RC, bool PF>
-__global__ void __launch_bounds__(NTHREADS, MINB) k_pivot_step(const TabDev *Tp, Rec *rec, int do_select) {
+__global__ void __launch_bounds__(NTHREADS, MINB)
+    k_pivot_step(const TabDev *Tp, Rec *rec, int do_select, const double *prow_arg, int stride_arg) {
     extern __shared__ __align__(128) double frow[];
     __shared__ TabDev T;
     __shared__ SelSmem sel;
     __shared__ uint64_t bar;
     __shared__ int s_last;
-    const int tid = threadIdx.x;
-    if (rec->status != ST_RUNNING || !rec->has_pivot) return;
-    if (rec->stop_at >= 0 && rec->done >= rec->stop_at) return;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    // Programmatic dependent launch: let the next step's CTAs be scheduled while this grid drains,
+    // and do not touch anything the previous step wrote before it has completed.  Both are no-ops
+    // when the launch carries no programmatic dependency.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int status = rec->status, has_pivot = rec->has_pivot, stop_at = rec->stop_at, launch = rec->done;
+    if (status != ST_RUNNING || !has_pivot) return;
+    if (stop_at >= 0 && launch >= stop_at) return;
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, g0 = 0;
     if (tid == 0) {
-        T = *Tp;
+        t0 = clock64();
         mbar_init(&bar, 1);
         fence_mbar_init();
+        mbar_expect_tx(&bar, (uint32_t)stride_arg * 8u);
+        tma_bulk_g2s(frow, prow_arg, (uint32_t)stride_arg * 8u, &bar);  // raw pivot row -> smem (TMA)
+        T = *Tp;
     }
-    __syncthreads();
-    const bool dbg = T.dbg != nullptr && rec->done < T.dbg_cap;
-    if (dbg && tid == 0) {
-        t0 = clock64();
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
-    }
-    const int rstar = rec->r, cstar = rec->c, flush = rec->flush;
-    const int launch = rec->done;
+    const int rstar = rec->r, cstar = rec->c, flush = rec->flush, phase = rec->phase;
+    const int p1 = rec->p1, p2 = rec->p2, log_n0 = rec->log_n;
     const double q = rec->q;
-    const int next_c = rec->next_c, next_neg = rec->next_neg;
-    const bool stop_after = rec->stop_at >= 0 && rec->done + 1 >= rec->stop_at;
-    stage_pivot_row(T, frow, &bar, 0, cstar, q, flush);
-    if (dbg && tid == 0) t1 = clock64();
+    const int next_c = rec->next_c, next_neg = rec->next_neg, lookahead = rec->lookahead;
+    const bool stop_after = stop_at >= 0 && launch + 1 >= stop_at;
+    __syncthreads();
+    const bool dbg = T.dbg != nullptr && launch < T.dbg_cap;
+    if (dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
 
     const int G = gridDim.x, b = blockIdx.x;
     const int base = T.H / G, rem = T.H % G;
     const int r0 = b * base + min(b, rem);
     const int nr = base + (b < rem ? 1 : 0);
+    // look-ahead operands of this thread's row, loaded while the TMA copy is in flight
+    const bool fast = do_select && next_c >= 0 && !stop_after && nr <= NT;
+    const bool have = fast && next_c > 0 && tid < nr;
+    double la_coef = 0.0, la_col = 0.0, la_rhs = 0.0;
+    if (have) {
+        const size_t off = (size_t)(r0 + tid) * T.stride;
+        la_coef = T.pcol[r0 + tid];
+        la_col = ldg_cg(T.M + off + next_c);
+        la_rhs = ldg_cg(T.M + off);
+    }
+
+    mbar_wait(&bar, 0);
+    for (int c = tid; c < T.stride; c += NT) {  // normalise in place (simplex.ts:352-364, 380-382)
+        const double v = frow[c];
+        double f = nz16(v) ? v / q : 0.0;
+        if (c == cstar) f = 1.0 / q;
+        if (flush && !nz16(f) && f != 0.0) f = 0.0;
+        frow[c] = f;
+    }
+    __syncthreads();
+    if (dbg && tid == 0) t1 = clock64();
+
     update_rows<RC, PF>(T, frow, r0, nr, rstar, cstar, q, b == G - 1);
     if (dbg && tid == 0) t2 = clock64();
 
-    const bool fast = do_select && next_c >= 0 && !stop_after;
     if (fast && next_c > 0) {
-        __syncthreads();  // this CTA's rows are written: read them back for the look-ahead ratio test
-        cta_ratio_partial(T, sel, r0, nr, next_c, next_neg);
+        __syncthreads();  // every warp is done reading this CTA's pcol entries before they are replaced
+        const bool is_prow = (r0 + tid) == rstar;
+        const double col = new_entry(la_col, is_prow, la_coef, frow[next_c], next_c == cstar, q);
+        const double rhs = new_entry(la_rhs, is_prow, la_coef, frow[0], false, q);
+        cta_ratio_partial(T, sel, r0, nr, have, col, rhs, next_neg);
     }
     __threadfence();
     __syncthreads();
@@ -321,18 +368,18 @@ __global__ void __launch_bounds__(NTHREADS, MINB) k_pivot_step(const TabDev *Tp,
         __threadfence();
         if (tid == 0) {
             rec->ticket = 0;
-            rec->done += 1;
-            if (rec->phase == 1) rec->p1 += 1; else rec->p2 += 1;
+            rec->done = launch + 1;
+            if (phase == 1) rec->p1 = p1 + 1; else rec->p2 = p2 + 1;
             rec->has_pivot = 0;
         }
-        __syncthreads();
         if (do_select && !stop_after) {
             if (fast) {
-                cta_tail_lookahead(T, rec, sel, G);
+                cta_tail_lookahead(T, rec, sel, G, next_c, next_neg, log_n0);
             } else {
+                __syncthreads();
                 cta_select<true>(T, rec, sel);
                 __syncthreads();
-                if (rec->lookahead && rec->has_pivot && rec->phase == 2 && T.nOpt == 0) cta_price_next(T, rec, sel);
+                if (lookahead && rec->has_pivot && rec->phase == 2 && T.nOpt == 0) cta_price_next(T, rec, sel);
             }
         }
     }
@@ -344,4 +391,3 @@ __global__ void __launch_bounds__(NTHREADS, MINB) k_pivot_step(const TabDev *Tp,
         d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = s_last; d[7] = nr;
     }
 }
-

@@ -119,7 +119,9 @@ class GpuTableau:
         self.bestCuts: list = []
         self.engine = 0
         self.max_spec_batch = 0
+        self.distributed = False  # True: branchAndCut shards node rounds over torch.distributed ranks
         self._cache: dict = {}
+        self._cache_log = None
 
     # name-mangling-free accessor used by Solve (main.ts:180)
     @property
@@ -173,6 +175,7 @@ class GpuTableau:
         if self.engine:
             self.set_option(_lib.OPT_ENGINE, self.engine)
         self._cache.clear()
+        self._cache_log = None
         return self
 
     def setModel(self, model) -> "GpuTableau":  # tableau.ts:382-391
@@ -297,6 +300,12 @@ class GpuTableau:
         opts.check_cycles = self._check_cycles()
         opts.max_spec_batch = int(self.max_spec_batch)
         opts.rank, opts.n_ranks = 0, 1
+        keep = None
+        if self.distributed:  # shard each round's nodes over ranks (one process per GPU)
+            from . import distributed as D
+            if D.is_active():
+                opts.rank, opts.n_ranks = D.rank_and_world()
+                opts.all_gather, keep = D.make_all_gather_hook()
         opts.max_nodes = int(getattr(m, "max_nodes", 0) or 0)
         st = BnbStatus()
         cap = 4096
@@ -392,12 +401,18 @@ class GpuTableau:
         return self._download("opt")
 
     def pivot_log(self) -> np.ndarray:
+        """All pivots executed on this tableau since upload (row, col, leaving var, entering var);
+        needs JSLP_OPT_PIVOT_LOG_CAP.  The library hands the log over in drains; they are
+        accumulated here."""
         n = C.c_int()
         L = self.context.lib
         cap = 1 << 20
         buf = np.empty((cap, 4), dtype=np.int32)
         _lib.check(L.jslp_pivot_log(self._h(), buf.ctypes.data, cap, C.byref(n)))
-        return buf[:min(cap, n.value)].copy()
+        new = buf[:min(cap, n.value)].copy()
+        old = self._cache_log if self._cache_log is not None else np.empty((0, 4), dtype=np.int32)
+        self._cache_log = np.concatenate([old, new]) if len(new) else old
+        return self._cache_log
 
     # ------------------------------------------------------------------ solve (tableau.ts:250-274)
     def updateVariableValues(self) -> None:  # dynamic-modification.ts:57-76

@@ -57,19 +57,21 @@ def main():
     g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, row_capacity=H)
     g.save()
     configs = []
-    for variant in range(7):
-        for look in (1, 0):
-            configs.append({"engine": 2, "variant": variant, "grid": 0, "look": look})
-    for grid in (1, 3, 4, 6, 8):
-        configs.append({"engine": 2, "variant": 2, "grid": grid, "look": 1})
-        configs.append({"engine": 2, "variant": 5, "grid": grid, "look": 1})
-    configs.append({"engine": 1, "variant": 0, "grid": 0, "look": 0})
+    for variant in (0, 3, 1, 2, 4, 6):
+        for pdl in (0, 1):
+            configs.append({"engine": 2, "variant": variant, "grid": 0, "look": 1, "pdl": pdl})
+    configs.append({"engine": 2, "variant": 0, "grid": 0, "look": 0, "pdl": 0})
+    configs.append({"engine": 2, "variant": 0, "grid": 0, "look": 0, "pdl": 1})
+    configs.append({"engine": 2, "variant": 0, "grid": 1, "look": 1, "pdl": 1})
+    configs.append({"engine": 2, "variant": 2, "grid": 3, "look": 1, "pdl": 1})
+    configs.append({"engine": 1, "variant": 0, "grid": 0, "look": 0, "pdl": 0})
     results = []
     for cfg in configs:
         g.set_option(_lib.OPT_ENGINE, cfg["engine"])
         g.set_option(_lib.OPT_STEP_VARIANT, cfg["variant"])
         g.set_option(_lib.OPT_GRID_PER_SM, cfg["grid"])
         g.set_option(_lib.OPT_LOOKAHEAD, cfg["look"])
+        g.set_option(_lib.OPT_PDL, cfg["pdl"])
         g.set_option(_lib.OPT_TIMELINE, 0)
         best = None
         for rep in range(3):

@@ -14,7 +14,7 @@ ASSIGNMENT_UNCONFIRMED = {"StockCuttingProblem.json", "Vendor Selection.json"}
 # engine, or (engine, look-ahead tail on/off, fused-step kernel variant)
 ENGINES = {"two_kernel": 1, "fused": 2, "resident": 4, "fused_generic_tail": (2, 0, 0),
            "fused_v1_prefetch": (2, 1, 1), "fused_v2_occ4": (2, 1, 2), "fused_v3_t512": (2, 1, 3),
-           "fused_v5_t128": (2, 1, 5)}
+           "fused_v5_t128": (2, 1, 5), "fused_pdl": (2, 1, 0, 1), "fused_generic_pdl": (2, 0, 3, 1)}
 
 
 def same_bits(a, b):
@@ -38,9 +38,10 @@ def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
     """engine: JSLP_OPT_ENGINE value, or a tuple (engine, lookahead, step variant)."""
     from jslpsolver_b200 import _lib
     from jslpsolver_b200.tableau import GpuTableau
-    lookahead = variant = None
+    lookahead = variant = pdl = None
     if isinstance(engine, tuple):
-        engine, lookahead, variant = engine
+        engine, lookahead, variant = engine[:3]
+        pdl = engine[3] if len(engine) > 3 else None
     g = GpuTableau(precision)
     g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, it.unrestricted, it.integerIndices, it.optionalCosts)
     g.set_option(_lib.OPT_ENGINE, engine)
@@ -49,6 +50,8 @@ def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
         g.set_option(_lib.OPT_LOOKAHEAD, lookahead)
     if variant is not None:
         g.set_option(_lib.OPT_STEP_VARIANT, variant)
+    if pdl is not None:
+        g.set_option(_lib.OPT_PDL, pdl)
     if batch:
         g.set_option(_lib.OPT_BATCH, batch)
     return g
