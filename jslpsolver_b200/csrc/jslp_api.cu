@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace jslp;
@@ -125,8 +126,10 @@ struct jslp_tab {
     // graphs
     cudaGraphExec_t g_fused = nullptr, g_simple = nullptr;
     int g_batch = 0, g_grid = 0, g_smem = 0;
+    cudaGraphExec_t g_fused_small = nullptr, g_simple_small = nullptr;  // first batch of every solve
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};
     Saved saved;
-    Snapshot snap;
+    Snapshot snaps[2];  // one restart point per in-flight batch
     std::vector<NodeLogEntry> node_log;
     ResidentBufs rbufs;
 };
@@ -180,7 +183,9 @@ extern "C" int jslp_ctx_sync(jslp_ctx *c) {
 static void drop_graphs(jslp_tab *t) {
     if (t->g_fused) cudaGraphExecDestroy(t->g_fused);
     if (t->g_simple) cudaGraphExecDestroy(t->g_simple);
-    t->g_fused = t->g_simple = nullptr;
+    if (t->g_fused_small) cudaGraphExecDestroy(t->g_fused_small);
+    if (t->g_simple_small) cudaGraphExecDestroy(t->g_simple_small);
+    t->g_fused = t->g_simple = t->g_fused_small = t->g_simple_small = nullptr;
 }
 
 static int push_desc(jslp_tab *t) {
@@ -240,8 +245,10 @@ extern "C" int jslp_tab_create(jslp_ctx *ctx, int width, int height, int row_cap
     CK(cudaMalloc(&t->d_T, sizeof(TabDev)));
     CK(cudaMalloc(&t->d_rec, sizeof(Rec)));
     CK(cudaMalloc(&t->d_mip, sizeof(MipOut)));
-    CK(cudaMallocHost(&t->h_rec, sizeof(Rec)));
-    CK(cudaMallocHost(&t->h_log, sizeof(int4) * (size_t)t->hd.plog_cap));
+    CK(cudaMallocHost(&t->h_rec, sizeof(Rec) * 2));  // two read-back slots: batches are double-buffered
+    CK(cudaMallocHost(&t->h_log, sizeof(int4) * 2 * (size_t)t->hd.plog_cap));
+    CK(cudaEventCreateWithFlags(&t->ev_slot[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&t->ev_slot[1], cudaEventDisableTiming));
     CK(cudaMallocHost(&t->h_mip, sizeof(MipOut)));
     CK(cudaMemsetAsync(t->d_rec, 0, sizeof(Rec), ctx->stream));
     CK(cudaMemsetAsync(t->hd.prow, 0, sizeof(double) * (size_t)t->stride, ctx->stream));
@@ -279,7 +286,10 @@ extern "C" void jslp_tab_destroy(jslp_tab *t) {
     cudaFree(t->d_T); cudaFree(t->d_rec); cudaFree(t->d_mip); cudaFree(t->d_cuts);
     cudaFreeHost(t->h_rec); cudaFreeHost(t->h_log); cudaFreeHost(t->h_mip); cudaFreeHost(t->h_cuts);
     free_saved(t->saved);
-    free_snap(t->snap);
+    free_snap(t->snaps[0]);
+    free_snap(t->snaps[1]);
+    if (t->ev_slot[0]) cudaEventDestroy(t->ev_slot[0]);
+    if (t->ev_slot[1]) cudaEventDestroy(t->ev_slot[1]);
     t->rbufs.release();
     delete t;
 }
@@ -407,6 +417,7 @@ static const StepVariant STEP_VARIANTS[] = {
     {k_pivot_step<256, 4, 2, true>, 256, 4, "t256 occ4 rc2 prefetch"},
 };
 static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VARIANTS[0]));
+static const int SMALL_BATCH = 24;  // steps in the first graph of a solve
 
 static const StepVariant &step_variant(const jslp_tab *t) { return STEP_VARIANTS[t->variant]; }
 
@@ -451,13 +462,14 @@ static int build_graphs(jslp_tab *t) {
     cudaStream_t s = t->ctx->stream;
     const StepVariant &sv = step_variant(t);
     CK(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    for (int mode = 0; mode < 2; mode++) {
+    for (int mode = 0; mode < 4; mode++) {  // {fused, two-kernel} x {long batch, short first batch}
+        const int nsteps = mode >= 2 ? SMALL_BATCH : t->batch;
         cudaGraph_t g;
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
-        if (mode == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
+        if ((mode & 1) == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
             k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-            for (int i = 0; i < t->batch; i++) {
+            for (int i = 0; i < nsteps; i++) {
                 if (t->pdl && i > 0) {
                     // programmatic dependent launch: step i's CTAs are scheduled while step i-1
                     // drains and block in griddepcontrol.wait until it has completed
@@ -482,7 +494,7 @@ static int build_graphs(jslp_tab *t) {
                 }
             }
         } else {  // two kernels per pivot
-            for (int i = 0; i < t->batch; i++) {
+            for (int i = 0; i < nsteps; i++) {
                 k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
                 sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0, t->hd.prow, t->stride);
             }
@@ -493,7 +505,8 @@ static int build_graphs(jslp_tab *t) {
         e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-        if (mode == 0) t->g_fused = ge; else t->g_simple = ge;
+        if (mode == 0) t->g_fused = ge; else if (mode == 1) t->g_simple = ge;
+        else if (mode == 2) t->g_fused_small = ge; else t->g_simple_small = ge;
     }
     t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * t->pdl;
     return JSLP_OK;
@@ -529,8 +542,33 @@ static bool cycle_hit(const std::vector<long long> &h, int *start, int *len) {
     return false;
 }
 
-static int ensure_snapshot(jslp_tab *t) {
-    Snapshot &sn = t->snap;
+// The same test in O(occurrences of the newest pair) per push instead of O(n): a block of length L
+// that repeats up to the newest element needs h[n-1-L] == h[n-1], so only earlier positions of the
+// newest pair are candidate block ends (largest L first, as the literal scan reports it).
+struct CycleHist {
+    std::vector<long long> h;
+    std::unordered_map<long long, std::vector<int>> pos;
+    bool push_and_check(long long v, int *start, int *len) {
+        h.push_back(v);
+        const long n = (long)h.size();
+        std::vector<int> &p = pos[v];
+        bool hit = false;
+        for (size_t k = 0; k < p.size() && !hit; k++) {
+            const long L = (n - 1) - p[k];
+            if (2 * L > n) continue;
+            const long e1 = n - 2 * L, e2 = n - L;
+            bool eq = true;
+            for (long i = 0; i < L; i++)
+                if (h[e1 + i] != h[e2 + i]) { eq = false; break; }
+            if (eq) { *start = (int)e1; *len = (int)L; hit = true; }
+        }
+        p.push_back((int)(n - 1));
+        return hit;
+    }
+};
+
+static int ensure_snapshot(jslp_tab *t, int slot) {
+    Snapshot &sn = t->snaps[slot];
     if (sn.M && sn.rowcap == t->rowcap) return JSLP_OK;
     free_snap(sn);
     CK(cudaMalloc(&sn.M, sizeof(double) * (size_t)t->rowcap * t->stride));
@@ -547,8 +585,8 @@ static int ensure_snapshot(jslp_tab *t) {
     return JSLP_OK;
 }
 
-static int snapshot_copy(jslp_tab *t, bool to_snapshot) {
-    Snapshot &sn = t->snap;
+static int snapshot_copy(jslp_tab *t, int slot, bool to_snapshot) {
+    Snapshot &sn = t->snaps[slot];
     cudaStream_t s = t->ctx->stream;
     auto cp = [&](void *live, void *snap, size_t bytes) {
         return to_snapshot ? cudaMemcpyAsync(snap, live, bytes, cudaMemcpyDeviceToDevice, s)
@@ -582,7 +620,6 @@ static void fill_status(jslp_tab *t, jslp_lp_status *o, const Rec &r, int cycled
 }
 
 static size_t node_smem_bytes(int Hcap, int W, int *Ws_out);
-static int ensure_snapshot(jslp_tab *t);
 static void finish_lp_flags(jslp_tab *t, int only_phase, int cycled, const Rec &last);
 
 // Engine 4: the whole simplex() of a small tableau in ONE launch, tableau resident in shared
@@ -596,8 +633,9 @@ static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, b
     int Ws = 0;
     const size_t smem = node_smem_bytes(t->H, t->W, &Ws);
     if (t->nOpt > 0 || smem > (size_t)ctx->max_smem_optin - 2048) return JSLP_OK;
-    int rc = ensure_snapshot(t);
+    int rc = ensure_snapshot(t, 0);
     if (rc) return rc;
+    const Snapshot &snap = t->snaps[0];
     const int log_cap = 2048;
     rc = t->rbufs.ensure(1, 0, log_cap);
     if (rc) return rc;
@@ -610,7 +648,7 @@ static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, b
     memset(&nb, 0, sizeof(nb));
     nb.rootM = t->hd.M; nb.root_vrow = t->hd.vrow; nb.root_vcol = t->hd.vcol;
     nb.cuts = rb.d_cuts; nb.cut_off = rb.d_off; nb.results = rb.d_res; nb.logs = rb.d_logs;
-    nb.wb_M = t->snap.M; nb.wb_vrow = t->snap.vrow; nb.wb_vcol = t->snap.vcol;
+    nb.wb_M = snap.M; nb.wb_vrow = snap.vrow; nb.wb_vcol = snap.vcol;
     nb.H0 = t->H; nb.root_stride = t->stride; nb.first_index = t->lastElementIndex;
     nb.Hcap = t->H; nb.Ws = Ws; nb.log_cap = log_cap; nb.max_pivots = log_cap - 2;
     if ((int)smem > rb.smem_set) {
@@ -635,10 +673,10 @@ static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, b
         }
     }
     // adopt the result
-    CK(cudaMemcpy2DAsync(t->hd.M, sizeof(double) * t->stride, t->snap.M, sizeof(double) * t->stride,
+    CK(cudaMemcpy2DAsync(t->hd.M, sizeof(double) * t->stride, snap.M, sizeof(double) * t->stride,
                          sizeof(double) * t->W, t->H, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(t->hd.vrow, t->snap.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(t->hd.vcol, t->snap.vcol, sizeof(int) * (size_t)t->W, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vrow, snap.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vcol, snap.vcol, sizeof(int) * (size_t)t->W, cudaMemcpyDeviceToDevice, s));
     float ms = 0.f;
     if (timed) {
         CK(cudaEventRecord(ctx->ev1, s));
@@ -673,9 +711,13 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     rc = build_graphs(t);
     if (rc) return rc;
     const int engine = (t->engine == 1) ? 1 : 2;
-    cudaGraphExec_t graph = engine == 1 ? t->g_simple : t->g_fused;
-    const int64_t launches_per_batch = engine == 1 ? 1 + 2 * (int64_t)t->batch : 2 + (int64_t)t->batch;
+    // the first batch of a solve is short (most node LPs end inside it); later ones are long
+    cudaGraphExec_t graphs[2] = {engine == 1 ? t->g_simple_small : t->g_fused_small,
+                                 engine == 1 ? t->g_simple : t->g_fused};
+    const int sizes[2] = {SMALL_BATCH, t->batch};
+    auto launches_of = [&](int k) { return engine == 1 ? 1 + 2 * (int64_t)sizes[k] : 2 + (int64_t)sizes[k]; };
     const int64_t launches0 = ctx->launches;
+    const int cap = t->hd.plog_cap;
 
     Rec init;
     memset(&init, 0, sizeof(init));
@@ -693,65 +735,95 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
 
     if (only_phase != 2) t->bounded = 1;  // simplex.ts:15
     if (check_cycles) {
-        rc = ensure_snapshot(t);
+        rc = ensure_snapshot(t, 0);
+        if (rc) return rc;
+        rc = ensure_snapshot(t, 1);
         if (rc) return rc;
     }
-    std::vector<long long> hist1, hist2;  // (leaving, entering) per phase call
-    long selected = 0;                    // selections seen so far in this call
+    CycleHist hist[2];   // (leaving, entering) per phase call (simplex.ts:27,102)
+    long selected = 0;   // selections seen so far in this call
     int cycled = 0, cyc_start = 0, cyc_len = 0;
     Rec last = init;
-    for (;;) {
+    // Batches are double-buffered: batch i+1 is enqueued before the host waits for batch i, so the
+    // read-back, the cycle check and the launch latency hide behind device work.  Kernels of a batch
+    // enqueued after the solve has finished exit at once.
+    int kind_of[2] = {0, 0};
+    auto enqueue = [&](int slot, int kind) -> int {
         if (check_cycles) {
-            rc = snapshot_copy(t, true);
+            int e = snapshot_copy(t, slot, true);
+            if (e) return e;
+        }
+        CK(cudaGraphLaunch(graphs[kind], s));
+        ctx->launches += launches_of(kind);
+        CK(cudaMemcpyAsync(t->h_rec + slot, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(t->h_log + (size_t)slot * cap, t->hd.plog, sizeof(int4) * (size_t)cap, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(t->ev_slot[slot], s));
+        kind_of[slot] = kind;
+        return JSLP_OK;
+    };
+    rc = enqueue(0, 0);
+    if (rc) return rc;
+    for (int i = 0;; i++) {
+        const int slot = i & 1;
+        const bool ahead = i >= 1;  // speculate only once a solve has outlived its first batch
+        if (ahead) {
+            rc = enqueue(slot ^ 1, 1);
             if (rc) return rc;
         }
-        CK(cudaGraphLaunch(graph, s));
-        ctx->launches += launches_per_batch;
-        CK(cudaMemcpyAsync(t->h_rec, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(t->h_log, t->hd.plog, sizeof(int4) * (size_t)t->hd.plog_cap, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        last = *t->h_rec;
-        const int n_new = std::min(last.log_n, t->hd.plog_cap);
-        if (last.log_n > t->hd.plog_cap) return fail(JSLP_E_CAPACITY, "pivot log overflow inside one batch");
+        CK(cudaEventSynchronize(t->ev_slot[slot]));
+        last = t->h_rec[slot];
+        const int4 *log = t->h_log + (size_t)slot * cap;
+        const int n_new = std::min(last.log_n, cap);
+        if (last.log_n > cap) return fail(JSLP_E_CAPACITY, "pivot log overflow inside one batch");
         long hit_at = -1;
         if (check_cycles) {
-            for (int i = 0; i < n_new; i++) {
-                const int4 e = t->h_log[i];
+            for (int k = 0; k < n_new; k++) {
+                const int4 e = log[k];
                 const int phase = (e.x >> 30) & 1 ? 2 : 1;
-                std::vector<long long> &h = phase == 1 ? hist1 : hist2;
-                h.push_back(((long long)e.z << 32) | (unsigned int)e.w);
-                if (cycle_hit(h, &cyc_start, &cyc_len)) { cycled = phase; hit_at = selected + i; break; }
+                if (hist[phase - 1].push_and_check(((long long)e.z << 32) | (unsigned int)e.w, &cyc_start, &cyc_len)) {
+                    cycled = phase;
+                    hit_at = selected + k;
+                    break;
+                }
             }
         }
         if (hit_at >= 0) {
             // The reference returns before executing the pivot that completes the repeat: replay
             // this batch from its snapshot and stop after `hit_at` executed pivots.
-            rc = snapshot_copy(t, false);
-            if (rc) return rc;
-            CK(cudaMemcpyAsync(t->h_rec, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            Rec r = *t->h_rec;
+            rc = snapshot_copy(t, slot, false);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(t->h_rec + slot, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            Rec r = t->h_rec[slot];
             // hit_at selections precede the offending one, so exactly hit_at pivots get executed;
             // a pivot pending in the snapshot was selected in an earlier batch, hence done < hit_at.
             r.stop_at = (int)hit_at;
-            *t->h_rec = r;
-            CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
+            t->h_rec[slot] = r;
+            CK(cudaMemcpyAsync(t->d_rec, t->h_rec + slot, sizeof(Rec), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
-            CK(cudaGraphLaunch(graph, s));
-            ctx->launches += launches_per_batch;
-            CK(cudaMemcpyAsync(t->h_rec, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
+            CK(cudaGraphLaunch(graphs[kind_of[slot]], s));
+            ctx->launches += launches_of(kind_of[slot]);
+            CK(cudaMemcpyAsync(t->h_rec + slot, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            last = *t->h_rec;
+            last = t->h_rec[slot];
             if (t->host_log_cap > 0)
-                for (long i = selected; i < hit_at && (int64_t)t->host_log.size() < t->host_log_cap; i++)
-                    t->host_log.push_back(t->h_log[i - selected]);
+                for (long k = selected; k < hit_at && (int64_t)t->host_log.size() < t->host_log_cap; k++)
+                    t->host_log.push_back(log[k - selected]);
             break;
         }
         if (t->host_log_cap > 0)
-            for (int i = 0; i < n_new && (int64_t)t->host_log.size() < t->host_log_cap; i++)
-                t->host_log.push_back(t->h_log[i]);
+            for (int k = 0; k < n_new && (int64_t)t->host_log.size() < t->host_log_cap; k++)
+                t->host_log.push_back(log[k]);
         selected += n_new;
-        if (last.status != ST_RUNNING) break;
+        if (last.status != ST_RUNNING) {
+            if (ahead) CK(cudaStreamSynchronize(s));  // drain the (no-op) batch that was enqueued ahead
+            break;
+        }
+        if (!ahead) {
+            rc = enqueue(slot ^ 1, 1);
+            if (rc) return rc;
+        }
     }
     float ms = 0.f;
     if (timed) {
@@ -876,7 +948,8 @@ static int grow_rows(jslp_tab *t, int need) {
     CK(cudaStreamSynchronize(t->ctx->stream));
     int rc = alloc_rows(t, cap);
     if (rc) return rc;
-    free_snap(t->snap);
+    free_snap(t->snaps[0]);
+    free_snap(t->snaps[1]);
     return JSLP_OK;  // descriptor is pushed by the caller; graphs read pointers through it
 }
 

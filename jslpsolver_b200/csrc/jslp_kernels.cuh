@@ -120,6 +120,8 @@ __device__ __forceinline__ bool better(const VI &b, const VI &a) {
 struct RedSmem {
     double v[32];
     int i[32];
+    int a[32];
+    int b[32];
 };
 
 // (value,index) arg-min / arg-max over the CTA, lowest index wins ties; result on every thread.
@@ -170,6 +172,117 @@ __device__ int block_reduce_int(int x, RedSmem &s) {
 
 __device__ __forceinline__ bool is_unres(const TabDev &T, int varIndex) {
     return T.unres != nullptr && varIndex >= 0 && varIndex < T.n_index && T.unres[varIndex] != 0;
+}
+
+// Ratio-test reduction in one pass (two barriers instead of six): min first-degenerate row,
+// (quotient,row) arg-min with lowest-row ties, count of non-zero pivot-column entries.
+__device__ __forceinline__ void block_reduce_ratio(int &dmin, VI &m, int &cnt, RedSmem &s) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        VI y;
+        y.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+        if (better<true>(y, m)) m = y;
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) { s.v[w] = m.v; s.i[w] = m.i; s.a[w] = dmin; s.b[w] = cnt; }
+    __syncthreads();
+    if (l < nw) { m.v = s.v[l]; m.i = s.i[l]; dmin = s.a[l]; cnt = s.b[l]; }
+    else { m.v = INFINITY; m.i = INT_MAX; dmin = INT_MAX; cnt = 0; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        VI y;
+        y.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+        if (better<true>(y, m)) m = y;
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+}
+
+// Copies the raw row `src` (W entries) into the stride-long side buffer `dst` (zero padded) with
+// all loads of a pass issued before its stores: the two may alias as far as the compiler knows,
+// and a load/store/load chain would cost one L2 round trip per element.
+template <bool GLOBAL>
+__device__ __forceinline__ void cta_copy_row(double *dst, const double *src, int W, int stride) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (int c0 = 0; c0 < stride; c0 += 8 * NT) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            v[k] = c < W ? ldt<GLOBAL>(src + c) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            if (c < stride) dst[c] = v[k];
+        }
+    }
+}
+
+// Updated cost entry of column c once the pivot (cstar, q) with cost-row coefficient coef0 has been
+// applied: the single-element form of update_rows for row 0.  v = raw pivot-row entry.
+__device__ __forceinline__ double priced_cost(double cost, double v, double coef0, bool nzc, bool is_pc, double q) {
+    if (nzc) {
+        if (is_pc) return -coef0 / q;
+        const double f = nz16(v) ? v / q : 0.0;
+        return nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
+    }
+    return (coef0 != 0.0 && is_pc) ? 0.0 : cost;
+}
+
+struct SelSmem {
+    RedSmem red;
+    int bc_col, bc_neg;
+};
+
+// Phase-2 pricing (simplex.ts:140-219, no optional objectives) in ONE pass over the cost row: the
+// reference scans 50-column batches left to right and stops at the first batch with an improving
+// column, taking the arg-max inside it; equivalently: lowest batch index that holds a candidate,
+// then (value, column) arg-max with lowest-column ties inside that batch.  PRICED = price the cost
+// row as the staged pivot (rowsrc, q, coef0, cstar) WILL leave it (look-ahead); new_label = label of
+// column cstar after that pivot's swap.  Result on every thread; *found = 0 when nothing prices in.
+template <bool GLOBAL, bool PRICED>
+__device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *rowsrc, double q, double coef0, int cstar,
+                               int new_label, int *found_out, int *neg_out) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int W = T.W;
+    const double prec = T.prec;
+    const bool nzc = nz16(coef0);
+    const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
+    int myb = INT_MAX, myneg = 0;
+    const VI init = {prec, INT_MAX};
+    VI x = init;
+#pragma unroll 4
+    for (int c = 1 + tid; c < W; c += NT) {
+        double nc = ldt<GLOBAL>(T.M + c);
+        if (PRICED) nc = priced_cost(nc, ldt<GLOBAL>(rowsrc + c), coef0, nzc, c == cstar, q);
+        bool un = false;
+        if (T.unres != nullptr && nc < 0) un = is_unres(T, (PRICED && c == cstar) ? new_label : T.vcol[c]);
+        const double v2 = un ? -nc : nc;
+        if (v2 > prec) {
+            const int b = (c - 1) / bsz;
+            if (b < myb) { myb = b; x.v = v2; x.i = c; myneg = un ? 1 : 0; }
+            else if (b == myb && v2 > x.v) { x.v = v2; x.i = c; myneg = un ? 1 : 0; }
+        }
+    }
+    const int bstar = block_reduce_int<0>(myb, s.red);
+    int found = 0;
+    if (bstar != INT_MAX) {
+        const int mine = (myb == bstar) ? x.i : INT_MAX;
+        VI y = (myb == bstar) ? x : init;
+        y = block_reduce_vi<false>(y, init, s.red);
+        found = y.i;
+        if (mine == y.i) s.bc_neg = myneg;  // exactly one thread owns the winning column
+    }
+    __syncthreads();
+    *found_out = found;
+    *neg_out = found > 0 ? s.bc_neg : 0;
+    __syncthreads();
 }
 
 // Literal, single-thread restatement of the pricing loop with optional objectives
@@ -232,11 +345,6 @@ __device__ void price_with_optional_seq(const TabDev &T, int *outCol, int *outNe
     *outNeg = isNeg;
 }
 
-struct SelSmem {
-    RedSmem red;
-    int bc_col, bc_neg;
-};
-
 // Stage pivot (rstar, cstar): raw pivot row -> prow, optional pivot-column entries, label swap,
 // pivot log, record.  `cnt` = number of rows r (incl. row 0 and rstar) with a non-zero
 // pivot-column entry; pcol must already be staged.
@@ -245,11 +353,11 @@ __device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar,
                                 int isneg, int cnt) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const double *prowsrc = T.M + (size_t)rstar * T.stride;
-    for (int c = tid; c < T.stride; c += NT) T.prow[c] = c < T.W ? ldt<GLOBAL>(prowsrc + c) : 0.0;
+    const double q = ldt<GLOBAL>(prowsrc + cstar);
+    const int leaving = T.vrow[rstar], entering = T.vcol[cstar];
+    cta_copy_row<GLOBAL>(T.prow, prowsrc, T.W, T.stride);
     for (int o = tid; o < T.nOpt; o += NT) T.optcoef[o] = ldt<GLOBAL>(T.opt + (size_t)o * T.stride + cstar);
     if (tid == 0) {
-        const double q = ldt<GLOBAL>(prowsrc + cstar);
-        const int leaving = T.vrow[rstar], entering = T.vcol[cstar];
         if (rec->log_n < T.plog_cap) T.plog[rec->log_n] = make_int4(rstar | (phase == 2 ? (1 << 30) : 0), cstar, leaving, entering);
         rec->log_n += 1;
         T.vrow[rstar] = entering;  // simplex.ts:339-349 (the inverse maps are rebuilt on read-back)
@@ -317,23 +425,9 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
 
     if (rstar < 0) {  // phase 2
         if (T.nOpt == 0) {
-            const int nColumns = W - 1;
-            const int bsz = T.use_partial ? T.batch_size : nColumns;
-            const int nb = T.use_partial ? (nColumns + bsz - 1) / bsz : 1;
-            const VI init = {prec, INT_MAX};
-            for (int b = 0; b < nb && cstar < 0; b++) {
-                const int start = 1 + b * bsz;
-                const int end = min(start + bsz - 1, W - 1);
-                VI x = init;
-                for (int c = start + tid; c <= end; c += NT) {
-                    const double rc = ldt<GLOBAL>(M + c);
-                    const double v = (rc < 0 && is_unres(T, T.vcol[c])) ? -rc : rc;
-                    if (v > x.v) { x.v = v; x.i = c; }
-                }
-                x = block_reduce_vi<false>(x, init, s.red);
-                if (x.i != INT_MAX) cstar = x.i;
-            }
-            if (cstar >= 0) isneg = (ldt<GLOBAL>(M + cstar) < 0 && is_unres(T, T.vcol[cstar])) ? 1 : 0;
+            int found, neg;
+            cta_price_scan<GLOBAL, false>(T, s, nullptr, 1.0, 0.0, -1, -1, &found, &neg);
+            if (found > 0) { cstar = found; isneg = neg; }
         } else {
             if (tid == 0) {
                 int c0, n0;
@@ -365,9 +459,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
             const double quo = isneg ? -rhs / col : rhs / col;
             if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
         }
-        dmin = block_reduce_int<0>(dmin, s.red);
-        m = block_reduce_vi<true>(m, init, s.red);
-        cnt = block_reduce_int<1>(cnt, s.red);
+        block_reduce_ratio(dmin, m, cnt, s.red);
         col_staged = true;
         if (dmin != INT_MAX) rstar = dmin;
         else if (m.i != INT_MAX) rstar = m.i;

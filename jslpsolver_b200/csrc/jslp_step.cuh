@@ -17,57 +17,9 @@
 // (included inside namespace jslp)
 
 // ---- pricing of the pivot AFTER the staged one (phase 2, no optional objectives) -------------
-// cost'[c] is the cost row as the staged pivot (rstar, cstar, q) will leave it; the expression must
-// be the very one update_rows evaluates for row 0, so the decision is bit-identical to pricing
-// afterwards.  rowsrc = raw pivot row (the prow side buffer or the tableau row itself).  All loads
-// of the first batch are issued before anything is consumed: one L2 round trip.
-// new_label = variable that labels column cstar after the pivot's swap (simplex.ts:339-343).
-__device__ __forceinline__ double priced_cost(double cost, double v, double coef0, bool nzc, bool is_pc, double q) {
-    if (nzc) {
-        if (is_pc) return -coef0 / q;
-        const double f = nz16(v) ? v / q : 0.0;
-        return nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
-    }
-    return (coef0 != 0.0 && is_pc) ? 0.0 : cost;
-}
-
-__device__ void cta_price_core(const TabDev &T, SelSmem &s, const double *rowsrc, double q, double coef0, int cstar,
-                               int new_label, int *found_out, int *neg_out) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int W = T.W;
-    const double prec = T.prec;
-    const bool nzc = nz16(coef0);
-    const int nColumns = W - 1;
-    const int bsz = T.use_partial ? T.batch_size : nColumns;
-    const int nb = T.use_partial ? (nColumns + bsz - 1) / bsz : 1;
-    const VI init = {prec, INT_MAX};
-    int found = -1;
-    for (int b = 0; b < nb && found < 0; b++) {
-        const int start = 1 + b * bsz;
-        const int end = min(start + bsz - 1, W - 1);
-        VI x = init;
-        int myneg = 0;
-        for (int c = start + tid; c <= end; c += NT) {
-            const double cost = ldg_cg(T.M + c);
-            const double v = ldg_cg(rowsrc + c);
-            const double nc = priced_cost(cost, v, coef0, nzc, c == cstar, q);
-            bool un = false;
-            if (T.unres != nullptr && nc < 0) un = is_unres(T, c == cstar ? new_label : T.vcol[c]);
-            const double v2 = un ? -nc : nc;
-            if (v2 > x.v) { x.v = v2; x.i = c; myneg = un ? 1 : 0; }
-        }
-        const int mine = x.i;
-        x = block_reduce_vi<false>(x, init, s.red);
-        if (x.i != INT_MAX) {
-            found = x.i;
-            if (mine == x.i) s.bc_neg = myneg;  // exactly one thread owns the winning column
-        }
-    }
-    __syncthreads();
-    *found_out = found > 0 ? found : 0;
-    *neg_out = found > 0 ? s.bc_neg : 0;
-    __syncthreads();
-}
+// cta_price_scan<true, true> (jslp_kernels.cuh) prices the cost row as the staged pivot will leave
+// it, with the very expression update_rows evaluates for row 0, so the decision is bit-identical
+// to pricing afterwards; one L2 round trip whatever the number of pricing batches.
 
 // Generic entry: the pivot is already staged (prow side buffer, labels swapped, rec filled).
 __device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
@@ -75,7 +27,7 @@ __device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
     const double q = rec->q;
     const double coef0 = ldg_cg(T.M + cstar);
     int found, neg;
-    cta_price_core(T, s, T.prow, q, coef0, cstar, T.vcol[cstar], &found, &neg);
+    cta_price_scan<true, true>(T, s, T.prow, q, coef0, cstar, T.vcol[cstar], &found, &neg);
     if (threadIdx.x == 0) { rec->next_c = found; rec->next_neg = neg; }
 }
 
@@ -219,9 +171,9 @@ __device__ __forceinline__ void cta_ratio_partial(const TabDev &T, SelSmem &s, i
             }
         }
     }
-    const int dall = block_reduce_int<0>(dmin, s.red);
-    const VI mall = block_reduce_vi<true>(m, init, s.red);
-    cnt = block_reduce_int<1>(cnt, s.red);
+    block_reduce_ratio(dmin, m, cnt, s.red);
+    const int dall = dmin;
+    const VI mall = m;
     Part *p = T.part + blockIdx.x;
     if (tid == 0) { p->minq = mall.v; p->minr = mall.i; p->dmin = dall; p->cnt = cnt; }
     (void)nr;
@@ -246,9 +198,9 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
         if (pd < dmin) dmin = pd;
         if (pr != INT_MAX && (pq < m.v || (pq == m.v && pr < m.i))) { m.v = pq; m.i = pr; }
     }
-    const int dall = block_reduce_int<0>(dmin, s.red);
-    const VI mall = block_reduce_vi<true>(m, init, s.red);
-    cnt = block_reduce_int<1>(cnt, s.red);
+    block_reduce_ratio(dmin, m, cnt, s.red);
+    const int dall = dmin;
+    const VI mall = m;
     int rstar;
     if (dall != INT_MAX) rstar = dall;
     else if (mall.i != INT_MAX) rstar = mall.i;
@@ -266,9 +218,9 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
     const double coef0 = ldg_cg(T.M + cn);
     const int leaving = T.vrow[rstar];
     const int entering = T.vcol[cn];
-    for (int c = tid; c < T.stride; c += NT) T.prow[c] = c < T.W ? ldg_cg(rowp + c) : 0.0;
+    cta_copy_row<true>(T.prow, rowp, T.W, T.stride);
     int found, neg;
-    cta_price_core(T, s, rowp, q, coef0, cn, leaving, &found, &neg);
+    cta_price_scan<true, true>(T, s, rowp, q, coef0, cn, leaving, &found, &neg);
     if (tid == 0) {
         if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rstar | (1 << 30), cn, leaving, entering);
         rec->log_n = log_n + 1;

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""MIP node-throughput report (BASELINE.json configs[3] and [4]); run under gpurun, optionally with
+torchrun for N > 1 (each round's nodes are sharded over ranks, summaries all-gathered over NCCL).
+
+  python scripts/mip_bench.py                       # 1 GPU
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/mip_bench.py
+
+Prints one JSON line per (workload, speculation width) from rank 0; also the oracle (CPU restatement of
+the reference, 1 thread) on the same models for the side-by-side number.
+"""
+import gzip
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import jslpsolver_b200 as J
+    from jslpsolver_b200 import problems
+    from helpers import strip_timeouts
+    from oracle import ref_model
+
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "sanity_fixtures.json.gz"), "rb") as f:
+        bundle = json.loads(f.read().decode())
+    farm = strip_timeouts([fx for fx in bundle["fixtures"] if fx["file"] == "LargeFarmMIP.json"][0]["model"])
+    nk = int(os.environ.get("KNAP_ITEMS", "1024"))
+    mk = int(os.environ.get("KNAP_CONS", "512"))
+    knap_nodes = int(os.environ.get("KNAP_NODES", "120"))
+    knap = problems.knapsack_mip_model(nk, mk, seed=12345)
+    workloads = [("LargeFarmMIP (36x101 root, tolerance 0.005)", farm, 0),
+                 (f"knapsack {nk} binaries x {mk} constraints (root {nk + mk + 1}x{nk + 1}), first {knap_nodes} nodes",
+                  knap, knap_nodes)]
+    widths = [int(x) for x in os.environ.get("SPEC", "1,8,32,128").split(",")]
+    for name, model, max_nodes in workloads:
+        # the knapsack root LP alone is ~85k pivots of 25 MB: minutes on one CPU core (measured in the
+        # build container: 159 s for root + 19 nodes); only the small workload is re-timed here
+        if rank == 0 and os.environ.get("NO_CPU", "0") != "1" and (max_nodes == 0 or os.environ.get("CPU_ALL") == "1"):
+            t0 = time.perf_counter()
+            osol = ref_model.solve_full(model, fast_cycles=True, max_nodes=max_nodes)
+            dt = time.perf_counter() - t0
+            st = osol.state
+            print(json.dumps({"impl": "oracle-cpu (1 thread)", "workload": name, "ms": 1e3 * dt,
+                              "iterations": st.bncIterations, "pivots": st.totalPivots,
+                              "node_lps_per_s": st.bncIterations / dt, "result": osol.evaluation}), flush=True)
+        for K in widths:
+            s = J.Solver()
+            s.max_spec_batch = K
+            inst = J.Model().loadJson(model)
+            inst.max_nodes = max_nodes
+            inst.tableau.distributed = world > 1
+            best = None
+            for rep in range(3):
+                inst = J.Model().loadJson(model)
+                inst.max_nodes = max_nodes
+                inst.tableau.distributed = world > 1
+                inst.tableau.max_spec_batch = K
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                sol = inst.solve()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                b = inst.tableau.lastBnbStatus
+                rec = {"impl": "b200", "n_gpus": world, "workload": name, "spec_width": K, "wall_ms": 1e3 * dt,
+                       "gpu_ms": b.gpu_ms, "iterations": b.iterations, "rounds": b.rounds,
+                       "node_lps": b.nodes_evaluated, "pivots": b.pivots, "launches": b.kernel_launches,
+                       "node_lps_per_s": b.nodes_evaluated * world / (b.gpu_ms * 1e-3) if world == 1 else None,
+                       "committed_nodes_per_s": b.iterations / (b.gpu_ms * 1e-3), "result": sol.evaluation}
+                if best is None or rec["gpu_ms"] < best["gpu_ms"]:
+                    best = rec
+            if rank == 0:
+                print(json.dumps(best), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,8 +40,9 @@ def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
     from jslpsolver_b200.tableau import GpuTableau
     lookahead = variant = pdl = None
     if isinstance(engine, tuple):
-        engine, lookahead, variant = engine[:3]
-        pdl = engine[3] if len(engine) > 3 else None
+        spec = engine
+        engine, lookahead, variant = spec[:3]
+        pdl = spec[3] if len(spec) > 3 else None
     g = GpuTableau(precision)
     g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, it.unrestricted, it.integerIndices, it.optionalCosts)
     g.set_option(_lib.OPT_ENGINE, engine)
