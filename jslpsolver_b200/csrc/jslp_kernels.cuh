@@ -257,17 +257,30 @@ __device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *rowsrc
     int myb = INT_MAX, myneg = 0;
     const VI init = {prec, INT_MAX};
     VI x = init;
-#pragma unroll 4
-    for (int c = 1 + tid; c < W; c += NT) {
-        double nc = ldt<GLOBAL>(T.M + c);
-        if (PRICED) nc = priced_cost(nc, ldt<GLOBAL>(rowsrc + c), coef0, nzc, c == cstar, q);
-        bool un = false;
-        if (T.unres != nullptr && nc < 0) un = is_unres(T, (PRICED && c == cstar) ? new_label : T.vcol[c]);
-        const double v2 = un ? -nc : nc;
-        if (v2 > prec) {
-            const int b = (c - 1) / bsz;
-            if (b < myb) { myb = b; x.v = v2; x.i = c; myneg = un ? 1 : 0; }
-            else if (b == myb && v2 > x.v) { x.v = v2; x.i = c; myneg = un ? 1 : 0; }
+    const bool has_unres = T.unres != nullptr;
+    // all loads of a pass are issued before any data-dependent branch: one L2 round trip per 8*NT columns
+    for (int c0 = 1; c0 < W; c0 += 8 * NT) {
+        double cv[8], rv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            cv[k] = c < W ? ldt<GLOBAL>(T.M + c) : 0.0;
+            rv[k] = (PRICED && c < W) ? ldt<GLOBAL>(rowsrc + c) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            if (c >= W) continue;
+            double nc = cv[k];
+            if (PRICED) nc = priced_cost(nc, rv[k], coef0, nzc, c == cstar, q);
+            bool un = false;
+            if (has_unres && nc < 0) un = is_unres(T, (PRICED && c == cstar) ? new_label : T.vcol[c]);
+            const double v2 = un ? -nc : nc;
+            if (v2 > prec) {
+                const int b = (c - 1) / bsz;
+                if (b < myb) { myb = b; x.v = v2; x.i = c; myneg = un ? 1 : 0; }
+                else if (b == myb && v2 > x.v) { x.v = v2; x.i = c; myneg = un ? 1 : 0; }
+            }
         }
     }
     const int bstar = block_reduce_int<0>(myb, s.red);
@@ -391,9 +404,18 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
     if (phase == 1) {
         const VI init = {-prec, INT_MAX};
         VI b = init;
-        for (int r = 1 + tid; r < H; r += NT) {
-            const double v = ldt<GLOBAL>(M + r * stride);
-            if (v < b.v) { b.v = v; b.i = r; }
+        for (int rbase = 1; rbase < H; rbase += 8 * NT) {
+            double rv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + tid + k * NT;
+                rv[k] = r < H ? ldt<GLOBAL>(M + r * stride) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + tid + k * NT;
+                if (r < H && rv[k] < b.v) { b.v = rv[k]; b.i = r; }
+            }
         }
         b = block_reduce_vi<true>(b, init, s.red);
         if (b.i == INT_MAX) {  // feasible (simplex.ts:51-54)
@@ -407,11 +429,24 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
             const VI einit = {-INFINITY, INT_MAX};
             VI e = einit;
             const double *lrow = M + rstar * stride;
-            for (int c = 1 + tid; c < W; c += NT) {
-                const double coef = ldt<GLOBAL>(lrow + c);
-                if (is_unres(T, T.vcol[c]) || coef < -prec) {
-                    const double quo = -ldt<GLOBAL>(M + c) / coef;
-                    if (e.v < quo) { e.v = quo; e.i = c; }
+            const bool has_unres = T.unres != nullptr;
+            for (int c0 = 1; c0 < W; c0 += 8 * NT) {  // loads of a pass first, then the tests
+                double kv[8], cv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int c = c0 + tid + k * NT;
+                    kv[k] = c < W ? ldt<GLOBAL>(lrow + c) : 0.0;
+                    cv[k] = c < W ? ldt<GLOBAL>(M + c) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int c = c0 + tid + k * NT;
+                    if (c >= W) continue;
+                    const double coef = kv[k];
+                    if ((has_unres && is_unres(T, T.vcol[c])) || coef < -prec) {
+                        const double quo = -cv[k] / coef;
+                        if (e.v < quo) { e.v = quo; e.i = c; }
+                    }
                 }
             }
             e = block_reduce_vi<false>(e, einit, s.red);
@@ -448,16 +483,27 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
         const VI init = {INFINITY, INT_MAX};
         VI m = init;
         int dmin = INT_MAX;
-        for (int r = tid; r < H; r += NT) {
-            const double col = ldt<GLOBAL>(M + r * stride + cstar);
-            T.pcol[r] = col;
-            if (nz16(col)) cnt++;
-            if (r == 0) continue;
-            if (-prec < col && col < prec) continue;
-            const double rhs = ldt<GLOBAL>(M + r * stride);
-            if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
-            const double quo = isneg ? -rhs / col : rhs / col;
-            if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+        for (int rbase = 0; rbase < H; rbase += 8 * NT) {  // loads of a pass first, then the tests
+            double cv[8], rv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + tid + k * NT;
+                cv[k] = r < H ? ldt<GLOBAL>(M + r * stride + cstar) : 0.0;
+                rv[k] = r < H ? ldt<GLOBAL>(M + r * stride) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + tid + k * NT;
+                if (r >= H) continue;
+                const double col = cv[k], rhs = rv[k];
+                T.pcol[r] = col;
+                if (nz16(col)) cnt++;
+                if (r == 0) continue;
+                if (-prec < col && col < prec) continue;
+                if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
+                const double quo = isneg ? -rhs / col : rhs / col;
+                if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+            }
         }
         block_reduce_ratio(dmin, m, cnt, s.red);
         col_staged = true;
@@ -475,10 +521,18 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
 
     if (!col_staged) {
         cnt = 0;
-        for (int r = tid; r < H; r += NT) {
-            const double col = ldt<GLOBAL>(M + r * stride + cstar);
-            T.pcol[r] = col;
-            if (nz16(col)) cnt++;
+        for (int rbase = 0; rbase < H; rbase += 8 * NT) {  // gather the pivot column: loads, then stores
+            double cv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + tid + k * NT;
+                cv[k] = r < H ? ldt<GLOBAL>(M + r * stride + cstar) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + tid + k * NT;
+                if (r < H) { T.pcol[r] = cv[k]; if (nz16(cv[k])) cnt++; }
+            }
         }
         cnt = block_reduce_int<1>(cnt, s.red);
     }

@@ -65,6 +65,11 @@ def main():
     configs.append({"engine": 2, "variant": 0, "grid": 1, "look": 1, "pdl": 1})
     configs.append({"engine": 2, "variant": 2, "grid": 3, "look": 1, "pdl": 1})
     configs.append({"engine": 1, "variant": 0, "grid": 0, "look": 0, "pdl": 0})
+    if os.environ.get("QUICK", "0") == "1":
+        configs = [{"engine": 2, "variant": 0, "grid": 0, "look": 1, "pdl": 0},
+                   {"engine": 2, "variant": 3, "grid": 0, "look": 1, "pdl": 0},
+                   {"engine": 2, "variant": 0, "grid": 0, "look": 0, "pdl": 0},
+                   {"engine": 1, "variant": 0, "grid": 0, "look": 0, "pdl": 0}]
     results = []
     for cfg in configs:
         g.set_option(_lib.OPT_ENGINE, cfg["engine"])
