@@ -82,7 +82,8 @@ enum {
     JSLP_OPT_GRID_PER_SM = 5,  /* CTAs per SM of the fused step, 0 = the variant's default        */
     JSLP_OPT_LOOKAHEAD = 6,    /* 1 (default) = look-ahead ratio test, 0 = generic serial tail    */
     JSLP_OPT_TIMELINE = 7,     /* record a per-CTA timeline for the first N launches of a solve   */
-    JSLP_OPT_PDL = 8           /* 1 = chain the fused steps with programmatic dependent launch    */
+    JSLP_OPT_PDL = 8,          /* 1 = chain the fused steps with programmatic dependent launch    */
+    JSLP_OPT_PINGPONG = 9      /* 1 (default) = ping-pong tableau + selector CTA, 0 = in-place    */
 };
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
 /* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */

@@ -10,7 +10,7 @@ from . import build as _build
 _LIB = None
 
 OPT_ENGINE, OPT_BATCH, OPT_PIVOT_LOG_CAP = 1, 2, 3
-OPT_STEP_VARIANT, OPT_GRID_PER_SM, OPT_LOOKAHEAD, OPT_TIMELINE, OPT_PDL = 4, 5, 6, 7, 8
+OPT_STEP_VARIANT, OPT_GRID_PER_SM, OPT_LOOKAHEAD, OPT_TIMELINE, OPT_PDL, OPT_PINGPONG = 4, 5, 6, 7, 8, 9
 ENGINE_AUTO, ENGINE_TWO_KERNEL, ENGINE_FUSED, ENGINE_PERSISTENT, ENGINE_RESIDENT = 0, 1, 2, 3, 4
 
 

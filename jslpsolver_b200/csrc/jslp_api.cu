@@ -120,7 +120,7 @@ struct jslp_tab {
     int isIntegralFlag = 0, bncIterations = 0;
     // options
     int engine = 0, batch = 256;
-    int variant = 0, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0;
+    int variant = 0, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0, pingpong = 1;
     int64_t host_log_cap = 0;
     std::vector<int4> host_log;
     // graphs
@@ -198,22 +198,24 @@ static int push_desc(jslp_tab *t) {
 
 static int alloc_rows(jslp_tab *t, int rowcap) {
     // (re)allocates every buffer whose size depends on the row capacity, preserving contents
-    double *M = nullptr, *pcol = nullptr;
+    double *M = nullptr, *M2 = nullptr, *pcol = nullptr;
     int *vrow = nullptr;
     CK(cudaMalloc(&M, sizeof(double) * (size_t)rowcap * t->stride));
+    CK(cudaMalloc(&M2, sizeof(double) * (size_t)rowcap * t->stride));  // ping-pong partner
     CK(cudaMalloc(&pcol, sizeof(double) * (size_t)rowcap));
     CK(cudaMalloc(&vrow, sizeof(int) * (size_t)rowcap));
     cudaStream_t s = t->ctx->stream;
     CK(cudaMemsetAsync(M, 0, sizeof(double) * (size_t)rowcap * t->stride, s));
+    CK(cudaMemsetAsync(M2, 0, sizeof(double) * (size_t)rowcap * t->stride, s));
     CK(cudaMemsetAsync(pcol, 0, sizeof(double) * (size_t)rowcap, s));
     CK(cudaMemsetAsync(vrow, 0xff, sizeof(int) * (size_t)rowcap, s));
     if (t->hd.M) {
         CK(cudaMemcpyAsync(M, t->hd.M, sizeof(double) * (size_t)t->H * t->stride, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(vrow, t->hd.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
         CK(cudaStreamSynchronize(s));
-        cudaFree(t->hd.M); cudaFree(t->hd.pcol); cudaFree(t->hd.vrow);
+        cudaFree(t->hd.M); cudaFree(t->hd.M2); cudaFree(t->hd.pcol); cudaFree(t->hd.vrow);
     }
-    t->hd.M = M; t->hd.pcol = pcol; t->hd.vrow = vrow;
+    t->hd.M = M; t->hd.M2 = M2; t->hd.pcol = pcol; t->hd.vrow = vrow;
     t->rowcap = rowcap;
     return JSLP_OK;
 }
@@ -239,6 +241,7 @@ extern "C" int jslp_tab_create(jslp_ctx *ctx, int width, int height, int row_cap
     if (rc) { delete t; return rc; }
     CK(cudaMalloc(&t->hd.vcol, sizeof(int) * (size_t)width));
     CK(cudaMalloc(&t->hd.prow, sizeof(double) * (size_t)t->stride));
+    CK(cudaMalloc(&t->hd.crow, sizeof(double) * (size_t)t->stride));
     CK(cudaMalloc(&t->hd.optflag, (size_t)width));
     t->hd.plog_cap = 4096;
     CK(cudaMalloc(&t->hd.plog, sizeof(int4) * (size_t)t->hd.plog_cap));
@@ -282,7 +285,7 @@ extern "C" void jslp_tab_destroy(jslp_tab *t) {
     cudaFree(t->hd.M); cudaFree(t->hd.vrow); cudaFree(t->hd.vcol); cudaFree(t->hd.unres);
     cudaFree(t->hd.opt); cudaFree(t->hd.prow); cudaFree(t->hd.pcol); cudaFree(t->hd.optcoef);
     cudaFree(t->hd.plog); cudaFree(t->hd.optflag); cudaFree(t->hd.intpos);
-    cudaFree(t->hd.part); cudaFree(t->hd.dbg);
+    cudaFree(t->hd.part); cudaFree(t->hd.dbg); cudaFree(t->hd.M2); cudaFree(t->hd.crow);
     cudaFree(t->d_T); cudaFree(t->d_rec); cudaFree(t->d_mip); cudaFree(t->d_cuts);
     cudaFreeHost(t->h_rec); cudaFreeHost(t->h_log); cudaFreeHost(t->h_mip); cudaFreeHost(t->h_cuts);
     free_saved(t->saved);
@@ -373,6 +376,9 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
         case JSLP_OPT_LOOKAHEAD:
             t->lookahead = value != 0;
             return JSLP_OK;
+        case JSLP_OPT_PINGPONG:
+            t->pingpong = value != 0;
+            return JSLP_OK;
         case JSLP_OPT_PDL:
             t->pdl = value != 0;
             return JSLP_OK;
@@ -401,7 +407,7 @@ extern "C" int jslp_debug_timeline(jslp_tab *t, int64_t *out, int64_t cap_values
 
 // ---------------------------------------------------------------------------------------------
 // Instantiations of the fused step: <threads, min CTAs/SM, rows per pass, software prefetch>.
-typedef void (*step_fn_t)(const TabDev *, Rec *, int, const double *, int);
+typedef void (*step_fn_t)(TabDev *, Rec *, int, const double *, int);
 struct StepVariant {
     step_fn_t fn;
     int threads, ctas_per_sm;
@@ -456,12 +462,14 @@ static int build_graphs(jslp_tab *t) {
     int rc = ensure_step_bufs(t, grid);
     if (rc) return rc;
     if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem &&
-        t->g_variant == t->variant + 100 * t->pdl)
+        t->g_variant == t->variant + 100 * t->pdl + 1000 * t->pingpong)
         return JSLP_OK;
     drop_graphs(t);
     cudaStream_t s = t->ctx->stream;
     const StepVariant &sv = step_variant(t);
     CK(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // 2 = ping-pong step: the last CTA of the grid is the selector (needs at least one row CTA besides it)
+    const int fused_mode = (t->pingpong && t->lookahead && grid >= 2) ? 2 : 1;
     for (int mode = 0; mode < 4; mode++) {  // {fused, two-kernel} x {long batch, short first batch}
         const int nsteps = mode >= 2 ? SMALL_BATCH : t->batch;
         cudaGraph_t g;
@@ -481,7 +489,7 @@ static int build_graphs(jslp_tab *t) {
                     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                     at[0].val.programmaticStreamSerializationAllowed = 1;
                     cfg.attrs = at; cfg.numAttrs = 1;
-                    const TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = 1; const double *a3 = t->hd.prow; int a4 = t->stride;
+                    TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = fused_mode; const double *a3 = t->hd.prow; int a4 = t->stride;
                     void *args[] = {&a0, &a1, &a2, &a3, &a4};
                     cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args);
                     if (le != cudaSuccess) {
@@ -490,7 +498,7 @@ static int build_graphs(jslp_tab *t) {
                         return fail(JSLP_E_CUDA, std::string("PDL launch: ") + cudaGetErrorString(le));
                     }
                 } else {
-                    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 1, t->hd.prow, t->stride);
+                    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, fused_mode, t->hd.prow, t->stride);
                 }
             }
         } else {  // two kernels per pivot
@@ -508,7 +516,7 @@ static int build_graphs(jslp_tab *t) {
         if (mode == 0) t->g_fused = ge; else if (mode == 1) t->g_simple = ge;
         else if (mode == 2) t->g_fused_small = ge; else t->g_simple_small = ge;
     }
-    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * t->pdl;
+    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * t->pdl + 1000 * t->pingpong;
     return JSLP_OK;
 }
 
@@ -592,7 +600,10 @@ static int snapshot_copy(jslp_tab *t, int slot, bool to_snapshot) {
         return to_snapshot ? cudaMemcpyAsync(snap, live, bytes, cudaMemcpyDeviceToDevice, s)
                            : cudaMemcpyAsync(live, snap, bytes, cudaMemcpyDeviceToDevice, s);
     };
-    CK(cp(t->hd.M, sn.M, sizeof(double) * (size_t)t->H * t->stride));
+    // the tableau itself: device-side copy of whichever ping-pong buffer is current at that point
+    k_copy_current<<<t->ctx->num_sms * 4, 256, 0, s>>>(t->d_T, sn.M, to_snapshot ? 1 : 0);
+    t->ctx->launches += 1;
+    CK(cudaGetLastError());
     CK(cp(t->hd.pcol, sn.pcol, sizeof(double) * (size_t)t->H));
     CK(cp(t->hd.vrow, sn.vrow, sizeof(int) * (size_t)t->H));
     CK(cp(t->hd.vcol, sn.vcol, sizeof(int) * (size_t)t->W));
@@ -825,12 +836,20 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             if (rc) return rc;
         }
     }
+    {   // the ping-pong step swaps TabDev.M / M2 on the device: adopt the device's view of "current"
+        TabDev cur;
+        CK(cudaMemcpyAsync(&cur, t->d_T, sizeof(TabDev), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        t->hd.M = cur.M;
+        t->hd.M2 = cur.M2;
+    }
     float ms = 0.f;
     if (timed) {
         CK(cudaEventRecord(ctx->ev1, s));
         CK(cudaEventSynchronize(ctx->ev1));
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     }
+    if (last.status == ST_ERROR) return fail(JSLP_E_CUDA, "ping-pong step: selector CTA timed out waiting for row CTAs");
 
     finish_lp_flags(t, only_phase, cycled, last);
     fill_status(t, out, last, cycled, cyc_start, cyc_len, ms, ctx->launches - launches0, engine);

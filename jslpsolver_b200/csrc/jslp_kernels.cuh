@@ -25,7 +25,7 @@
 
 namespace jslp {
 
-enum { ST_RUNNING = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_P1_DONE = 4 };
+enum { ST_RUNNING = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_P1_DONE = 4, ST_ERROR = 5 };
 
 struct Part;
 
@@ -43,6 +43,9 @@ struct TabDev {
     int4 *plog;            // per-batch pivot log (row, col, leaving var, entering var)
     unsigned char *optflag; // scratch [W] for the optional-objective tie-break lists
     int *intpos;           // position in model.integerVariables by var index, -1 otherwise [n_index]
+    double *M2;            // ping-pong partner of M (same shape): the fused ping-pong step reads M, writes
+                           // M2 and swaps the two pointers in this descriptor
+    double *crow;          // scratch: cost row as the pivot being staged will leave it [stride]
     Part *part;            // per-CTA look-ahead ratio-test partials [grid]
     long long *dbg;        // optional per-CTA timeline (8 x int64 per CTA per launch) or nullptr
     int W, H, stride, rowcap;
@@ -77,6 +80,7 @@ struct Rec {
     int unbounded_var;
     int only_phase;  // 0 = simplex(), 1 = phase1() only, 2 = phase2() only
     unsigned int ticket;
+    unsigned int arrive;  // ping-pong step: row CTAs that have published their ratio-test partial
     int lookahead;   // host switch: 1 = the tail also prices the pivot after next
     int next_c;      // entering column of the NEXT pivot, priced on the cost row as it will be after
                      // the staged pivot: -1 unknown (generic tail), 0 none (optimal), >0 column
@@ -245,10 +249,11 @@ struct SelSmem {
 // column, taking the arg-max inside it; equivalently: lowest batch index that holds a candidate,
 // then (value, column) arg-max with lowest-column ties inside that batch.  PRICED = price the cost
 // row as the staged pivot (rowsrc, q, coef0, cstar) WILL leave it (look-ahead); new_label = label of
-// column cstar after that pivot's swap.  Result on every thread; *found = 0 when nothing prices in.
+// column cstar after that pivot's swap; costsrc = the cost row to price (row 0 of the tableau, or a
+// scratch copy).  Result on every thread; *found = 0 when nothing prices in.
 template <bool GLOBAL, bool PRICED>
-__device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *rowsrc, double q, double coef0, int cstar,
-                               int new_label, int *found_out, int *neg_out) {
+__device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *costsrc, const double *rowsrc, double q,
+                               double coef0, int cstar, int new_label, int *found_out, int *neg_out) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int W = T.W;
     const double prec = T.prec;
@@ -264,7 +269,7 @@ __device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *rowsrc
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int c = c0 + tid + k * NT;
-            cv[k] = c < W ? ldt<GLOBAL>(T.M + c) : 0.0;
+            cv[k] = c < W ? ldt<GLOBAL>(costsrc + c) : 0.0;
             rv[k] = (PRICED && c < W) ? ldt<GLOBAL>(rowsrc + c) : 0.0;
         }
 #pragma unroll
@@ -461,7 +466,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
     if (rstar < 0) {  // phase 2
         if (T.nOpt == 0) {
             int found, neg;
-            cta_price_scan<GLOBAL, false>(T, s, nullptr, 1.0, 0.0, -1, -1, &found, &neg);
+            cta_price_scan<GLOBAL, false>(T, s, T.M, nullptr, 1.0, 0.0, -1, -1, &found, &neg);
             if (found > 0) { cstar = found; isneg = neg; }
         } else {
             if (tid == 0) {
@@ -700,6 +705,18 @@ __global__ void k_pack_rows(double *dst, int dstride, const double *src, int sst
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (zero_pad ? dstride : cols); c += gridDim.x * blockDim.x)
         dst[(size_t)r * dstride + c] = c < cols ? src[(size_t)r * sstride + c] : 0.0;
 }
+// Snapshot / restore of the CURRENT tableau buffer.  The ping-pong step swaps TabDev.M / M2 on the
+// device, so a host-side memcpy enqueued ahead of time cannot know which buffer will be current.
+__global__ void __launch_bounds__(256) k_copy_current(const TabDev *Tp, double *buf, int to_buf) {
+    const TabDev &T = *Tp;
+    const size_t n2 = ((size_t)T.H * T.stride) >> 1;  // stride is a multiple of 16 doubles
+    double2 *m = reinterpret_cast<double2 *>(T.M);
+    double2 *b = reinterpret_cast<double2 *>(buf);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        if (to_buf) b[i] = m[i]; else m[i] = b[i];
+    }
+}
+
 __global__ void k_gather_col(double *dst, const double *M, int stride, int rows, int col) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
         dst[r] = M[(size_t)r * stride + col];

@@ -27,7 +27,7 @@ __device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
     const double q = rec->q;
     const double coef0 = ldg_cg(T.M + cstar);
     int found, neg;
-    cta_price_scan<true, true>(T, s, T.prow, q, coef0, cstar, T.vcol[cstar], &found, &neg);
+    cta_price_scan<true, true>(T, s, T.M, T.prow, q, coef0, cstar, T.vcol[cstar], &found, &neg);
     if (threadIdx.x == 0) { rec->next_c = found; rec->next_neg = neg; }
 }
 
@@ -220,7 +220,7 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
     const int entering = T.vcol[cn];
     cta_copy_row<true>(T.prow, rowp, T.W, T.stride);
     int found, neg;
-    cta_price_scan<true, true>(T, s, rowp, q, coef0, cn, leaving, &found, &neg);
+    cta_price_scan<true, true>(T, s, T.M, rowp, q, coef0, cn, leaving, &found, &neg);
     if (tid == 0) {
         if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rstar | (1 << 30), cn, leaving, entering);
         rec->log_n = log_n + 1;
@@ -233,18 +233,191 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
     }
 }
 
+// =================================== ping-pong step ===================================================
+// The tableau is read from T.M and the updated tableau written to T.M2 (same traffic as in place:
+// every element is read once and written once), then the two pointers are swapped in the device
+// descriptor.  Because the old values stay readable for the whole launch there is no in-place
+// hazard left, and the serial work of choosing the next pivot moves OFF the critical path:
+//   * every row CTA publishes its look-ahead ratio-test partial BEFORE it starts streaming;
+//   * one extra CTA (the selector) waits for those G partials, reduces them to the next leaving
+//     row, derives that row and the cost row as this pivot will leave them from the OLD tableau
+//     (new_entry), stages the next pivot, prices the pivot after it and flips the descriptor --
+//     all while the row CTAs are still streaming.  The launch ends when the streaming ends.
+
+// dst rows [r0, r0+nr) = pivot applied to src rows (simplex.ts:352-391); every pair is written.
+template <int RC>
+__device__ __forceinline__ void update_rows_pp(const double *src, double *dst, int stride_i, const double *frow,
+                                               const double *s_coef, int r0, int nr, int rstar, int cstar, double q) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const size_t stride = (size_t)stride_i;
+    const int npair = stride_i >> 1;
+    const double2 *frow2 = reinterpret_cast<const double2 *>(frow);
+    const int cpair = cstar >> 1, codd = cstar & 1;
+    for (int rb = r0; rb < r0 + nr; rb += RC) {
+        double coef[RC];
+        bool valid[RC], act[RC], isp[RC];
+#pragma unroll
+        for (int j = 0; j < RC; j++) {
+            const int r = rb + j;
+            valid[j] = r < r0 + nr;
+            isp[j] = valid[j] && r == rstar;
+            coef[j] = (valid[j] && !isp[j]) ? s_coef[r - r0] : 0.0;
+            act[j] = valid[j] && !isp[j] && nz16(coef[j]);
+        }
+        const double *sb = src + (size_t)rb * stride;
+        double *db = dst + (size_t)rb * stride;
+        for (int c2 = tid; c2 < npair; c2 += NT) {
+            const double2 f = frow2[c2];
+            const bool z0 = nz16(f.x), z1 = nz16(f.y);
+            const bool pc = (c2 == cpair);
+            double2 old[RC];
+#pragma unroll
+            for (int j = 0; j < RC; j++)
+                if (valid[j] && !isp[j]) old[j] = ld_v2(sb + j * stride + 2 * c2);
+#pragma unroll
+            for (int j = 0; j < RC; j++) {
+                if (!valid[j]) continue;
+                double2 nv;
+                if (isp[j]) nv = f;                                                   // normalised pivot row
+                else if (act[j]) nv = upd2(old[j], f, z0, z1, coef[j], pc, codd, q);  // rank-1 update
+                else {                                                                // untouched row
+                    nv = old[j];
+                    if (pc && coef[j] != 0.0) { if (codd) nv.y = 0.0; else nv.x = 0.0; }  // simplex.ts:386-388
+                }
+                st_v2(db + j * stride + 2 * c2, nv);
+            }
+        }
+    }
+}
+
+// The selector CTA of a ping-pong step.  frow = normalised pivot row of the pivot being executed.
+__device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
+                                int rstar, int cstar, double q, int cn, int isneg, int launch, int p2, int log_n,
+                                bool stop_after) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const double *src = T.M;
+    // wait until every row CTA has published its partial (bounded spin: a lost arrival must not hang the GPU)
+    if (tid == 0) {
+        const long long tstart = clock64();
+        volatile unsigned int *arr = &rec->arrive;
+        bool ok = true;
+        while (*arr < (unsigned int)G) {
+            __nanosleep(40);
+            if (clock64() - tstart > 4000000000LL) { ok = false; break; }
+        }
+        s.bc_col = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s.bc_col) {
+        if (tid == 0) { rec->status = ST_ERROR; rec->has_pivot = 0; rec->arrive = 0; }
+        return;
+    }
+    __threadfence();
+    const double coef0 = ldg_cg(src + cstar);  // cost-row entry of the executing pivot's column
+    auto flip = [&]() {  // the updated tableau becomes the current one
+        Tp->M = T.M2;
+        Tp->M2 = T.M;
+    };
+    if (cn == 0 || stop_after) {  // optimal after this pivot (simplex.ts:265-269), or a replay stop
+        if (tid == 0) {
+            rec->arrive = 0;
+            rec->done = launch + 1; rec->p2 = p2 + 1; rec->has_pivot = 0;
+            if (!stop_after) {
+                rec->status = ST_OPTIMAL; rec->phase = 2;
+                rec->eval_raw = new_entry(ldg_cg(src), false, coef0, frow[0], false, q);
+            }
+            flip();
+        }
+        return;
+    }
+    const VI init = {INFINITY, INT_MAX};
+    VI m = init;
+    int dmin = INT_MAX, cnt = 0;
+    const volatile Part *parts = T.part;
+    for (int b = tid; b < G; b += NT) {
+        const double pq = parts[b].minq;
+        const int pr = parts[b].minr, pd = parts[b].dmin;
+        cnt += parts[b].cnt;
+        if (pd < dmin) dmin = pd;
+        if (pr != INT_MAX && (pq < m.v || (pq == m.v && pr < m.i))) { m.v = pq; m.i = pr; }
+    }
+    block_reduce_ratio(dmin, m, cnt, s.red);
+    int rnext;
+    if (dmin != INT_MAX) rnext = dmin;
+    else if (m.i != INT_MAX) rnext = m.i;
+    else {  // unbounded (simplex.ts:298-303)
+        if (tid == 0) {
+            rec->arrive = 0;
+            rec->done = launch + 1; rec->p2 = p2 + 1; rec->has_pivot = 0;
+            rec->status = ST_UNBOUNDED; rec->phase = 2;
+            rec->unbounded_var = T.vcol[cn];
+            rec->eval_raw = new_entry(ldg_cg(src), false, coef0, frow[0], false, q);
+            flip();
+        }
+        return;
+    }
+    // next pivot row and cost row as the executing pivot leaves them, from the old tableau
+    const double *rowp = src + (size_t)rnext * T.stride;
+    const bool is_prow = rnext == rstar;
+    const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
+    const int leaving = T.vrow[rnext];
+    const int entering = T.vcol[cn];
+    for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
+        double rv[8], cv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            rv[k] = c < T.W ? ldg_cg(rowp + c) : 0.0;
+            cv[k] = c < T.W ? ldg_cg(src + c) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            if (c >= T.stride) continue;
+            double ur = 0.0, uc = 0.0;
+            if (c < T.W) {
+                ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
+                uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
+            }
+            T.prow[c] = ur;
+            T.crow[c] = uc;
+        }
+    }
+    __syncthreads();
+    const double qn = ldg_cg(T.prow + cn);       // pivot element of the next pivot
+    const double coef0n = ldg_cg(T.crow + cn);   // its cost-row entry
+    int found, neg;
+    cta_price_scan<true, true>(T, s, T.crow, T.prow, qn, coef0n, cn, leaving, &found, &neg);
+    if (tid == 0) {
+        if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rnext | (1 << 30), cn, leaving, entering);
+        rec->log_n = log_n + 1;
+        T.vrow[rnext] = entering;  // simplex.ts:339-349
+        T.vcol[cn] = leaving;
+        rec->arrive = 0;
+        rec->done = launch + 1; rec->p2 = p2 + 1;
+        rec->phase = 2; rec->r = rnext; rec->c = cn; rec->q = qn; rec->is_neg = isneg;
+        rec->flush = (cnt - (nz16(qn) ? 1 : 0)) > 0;
+        rec->has_pivot = 1;
+        rec->next_c = found; rec->next_neg = neg;
+        flip();
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
-// do_select: 0 = update only (two-kernel engine), 1 = the last CTA selects the next pivot.
+// do_select: 0 = update only (two-kernel engine), 1 = the last CTA selects the next pivot,
+// 2 = ping-pong: the grid carries one extra CTA (the selector); steps that are not eligible for the
+// ping-pong path (phase 1, bootstrap, optional objectives) run in place on the first gridDim.x-1 CTAs.
 // prow_arg / stride_arg duplicate TabDev.prow / stride (both immutable after jslp_tab_create) so the
 // TMA copy of the pivot row can be issued before the descriptor has been fetched.
 template <int NTHREADS, int MINB, int RC, bool PF>
 __global__ void __launch_bounds__(NTHREADS, MINB)
-    k_pivot_step(const TabDev *Tp, Rec *rec, int do_select, const double *prow_arg, int stride_arg) {
+    k_pivot_step(TabDev *Tp, Rec *rec, int do_select, const double *prow_arg, int stride_arg) {
     extern __shared__ __align__(128) double frow[];
     __shared__ TabDev T;
     __shared__ SelSmem sel;
     __shared__ uint64_t bar;
     __shared__ int s_last;
+    __shared__ double s_coef[NTHREADS];
     const int tid = threadIdx.x, NT = blockDim.x;
     // Programmatic dependent launch: let the next step's CTAs be scheduled while this grid drains,
     // and do not touch anything the previous step wrote before it has completed.  Both are no-ops
@@ -272,12 +445,90 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     const bool dbg = T.dbg != nullptr && launch < T.dbg_cap;
     if (dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
 
-    const int G = gridDim.x, b = blockIdx.x;
+    const int b = blockIdx.x;
+    const int G = do_select == 2 ? (int)gridDim.x - 1 : (int)gridDim.x;  // row CTAs
     const int base = T.H / G, rem = T.H % G;
     const int r0 = b * base + min(b, rem);
-    const int nr = base + (b < rem ? 1 : 0);
+    const int nr = b < G ? base + (b < rem ? 1 : 0) : 0;
+    const bool rows_fit = base + 1 <= NT;  // one row per thread in the look-ahead (uniform over the grid)
+
+    // ------------------------------------------------------------------ ping-pong path
+    const bool pp = do_select == 2 && next_c >= 0 && phase == 2 && T.nOpt == 0 && T.M2 != nullptr && rows_fit;
+    if (pp) {
+        const bool want_partial = next_c > 0 && !stop_after;
+        double la_col = 0.0, la_rhs = 0.0, la_coef = 0.0;
+        if (tid < nr) {  // this thread's row: pivot-column entry, and the look-ahead operands
+            const size_t off = (size_t)(r0 + tid) * T.stride;
+            la_coef = ldg_cg(T.M + off + cstar);
+            if (want_partial) {
+                la_col = ldg_cg(T.M + off + next_c);
+                la_rhs = ldg_cg(T.M + off);
+            }
+            s_coef[tid] = la_coef;
+        }
+        mbar_wait(&bar, 0);
+        for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
+            const double v = frow[c];
+            double f = nz16(v) ? v / q : 0.0;
+            if (c == cstar) f = 1.0 / q;
+            if (flush && !nz16(f) && f != 0.0) f = 0.0;
+            frow[c] = f;
+        }
+        __syncthreads();
+        if (dbg && tid == 0) t1 = clock64();
+        if (b == G) {
+            cta_selector_pp(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after);
+            if (dbg && tid == 0) t2 = t3 = clock64();
+        } else {
+            if (want_partial) {  // ratio test of the NEXT pivot on this CTA's rows as this pivot leaves them
+                const bool is_prow = (r0 + tid) == rstar;
+                const double col = new_entry(la_col, is_prow, la_coef, frow[next_c], next_c == cstar, q);
+                const double rhs = new_entry(la_rhs, is_prow, la_coef, frow[0], false, q);
+                const double prec = T.prec;
+                VI m = {INFINITY, INT_MAX};
+                int dmin = INT_MAX, cnt = 0;
+                if (tid < nr) {
+                    const int r = r0 + tid;
+                    if (nz16(col)) cnt = 1;
+                    if (r != 0 && !(-prec < col && col < prec)) {
+                        if (col > 0 && prec > rhs && rhs > -prec) dmin = r;
+                        else {
+                            const double quo = next_neg ? -rhs / col : rhs / col;
+                            if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+                        }
+                    }
+                }
+                block_reduce_ratio(dmin, m, cnt, sel.red);
+                if (tid == 0) {
+                    Part *p = T.part + b;
+                    p->minq = m.v; p->minr = m.i; p->dmin = dmin; p->cnt = cnt;
+                }
+            }
+            if (tid == 0) {  // publish before streaming: the selector works while this CTA streams
+                __threadfence();
+                atomicAdd(&rec->arrive, 1u);
+            }
+            if (dbg && tid == 0) t2 = clock64();
+            update_rows_pp<RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
+            if (dbg && tid == 0) t3 = clock64();
+        }
+        if (dbg && tid == 0) {
+            t4 = clock64();
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long *d = T.dbg + ((size_t)launch * T.dbg_grid + b) * 8;
+            d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = (b == G); d[7] = nr;
+        }
+        return;
+    }
+    if (b >= G) {  // the selector CTA has nothing to do in an in-place step
+        mbar_wait(&bar, 0);  // ... but must not exit with its TMA copy still in flight
+        return;
+    }
+
+    // ------------------------------------------------------------------ in-place path
     // look-ahead operands of this thread's row, loaded while the TMA copy is in flight
-    const bool fast = do_select && next_c >= 0 && !stop_after && nr <= NT;
+    const bool fast = do_select && next_c >= 0 && !stop_after && rows_fit;
     const bool have = fast && next_c > 0 && tid < nr;
     double la_coef = 0.0, la_col = 0.0, la_rhs = 0.0;
     if (have) {

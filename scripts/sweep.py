@@ -66,12 +66,15 @@ def main():
     configs.append({"engine": 2, "variant": 2, "grid": 3, "look": 1, "pdl": 1})
     configs.append({"engine": 1, "variant": 0, "grid": 0, "look": 0, "pdl": 0})
     if os.environ.get("QUICK", "0") == "1":
-        configs = [{"engine": 2, "variant": 0, "grid": 0, "look": 1, "pdl": 0},
-                   {"engine": 2, "variant": 3, "grid": 0, "look": 1, "pdl": 0},
-                   {"engine": 2, "variant": 0, "grid": 0, "look": 0, "pdl": 0},
-                   {"engine": 1, "variant": 0, "grid": 0, "look": 0, "pdl": 0}]
+        configs = [{"engine": 2, "variant": 0, "grid": 0, "look": 1, "pdl": 0, "pp": 1},
+                   {"engine": 2, "variant": 0, "grid": 0, "look": 1, "pdl": 1, "pp": 1},
+                   {"engine": 2, "variant": 3, "grid": 0, "look": 1, "pdl": 0, "pp": 1},
+                   {"engine": 2, "variant": 2, "grid": 0, "look": 1, "pdl": 0, "pp": 1},
+                   {"engine": 2, "variant": 0, "grid": 0, "look": 1, "pdl": 0, "pp": 0},
+                   {"engine": 1, "variant": 0, "grid": 0, "look": 0, "pdl": 0, "pp": 0}]
     results = []
     for cfg in configs:
+        g.set_option(_lib.OPT_PINGPONG, cfg.get("pp", 1))
         g.set_option(_lib.OPT_ENGINE, cfg["engine"])
         g.set_option(_lib.OPT_STEP_VARIANT, cfg["variant"])
         g.set_option(_lib.OPT_GRID_PER_SM, cfg["grid"])

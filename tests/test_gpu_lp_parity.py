@@ -14,7 +14,8 @@ ASSIGNMENT_UNCONFIRMED = {"StockCuttingProblem.json", "Vendor Selection.json"}
 # engine, or (engine, look-ahead tail on/off, fused-step kernel variant)
 ENGINES = {"two_kernel": 1, "fused": 2, "resident": 4, "fused_generic_tail": (2, 0, 0),
            "fused_v1_prefetch": (2, 1, 1), "fused_v2_occ4": (2, 1, 2), "fused_v3_t512": (2, 1, 3),
-           "fused_v5_t128": (2, 1, 5), "fused_pdl": (2, 1, 0, 1), "fused_generic_pdl": (2, 0, 3, 1)}
+           "fused_v5_t128": (2, 1, 5), "fused_pdl": (2, 1, 0, 1), "fused_generic_pdl": (2, 0, 3, 1),
+           "fused_inplace": (2, 1, 0, 0, 0), "fused_inplace_v3": (2, 1, 3, 0, 0)}
 
 
 def same_bits(a, b):
@@ -38,11 +39,12 @@ def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
     """engine: JSLP_OPT_ENGINE value, or a tuple (engine, lookahead, step variant)."""
     from jslpsolver_b200 import _lib
     from jslpsolver_b200.tableau import GpuTableau
-    lookahead = variant = pdl = None
+    lookahead = variant = pdl = pingpong = None
     if isinstance(engine, tuple):
         spec = engine
         engine, lookahead, variant = spec[:3]
         pdl = spec[3] if len(spec) > 3 else None
+        pingpong = spec[4] if len(spec) > 4 else None
     g = GpuTableau(precision)
     g.upload(it.matrix, it.varIndexByRow, it.varIndexByCol, it.unrestricted, it.integerIndices, it.optionalCosts)
     g.set_option(_lib.OPT_ENGINE, engine)
@@ -53,6 +55,8 @@ def gpu_lp(it, engine, precision=1e-8, batch=None, log=1 << 16):
         g.set_option(_lib.OPT_STEP_VARIANT, variant)
     if pdl is not None:
         g.set_option(_lib.OPT_PDL, pdl)
+    if pingpong is not None:
+        g.set_option(_lib.OPT_PINGPONG, pingpong)
     if batch:
         g.set_option(_lib.OPT_BATCH, batch)
     return g
