@@ -242,6 +242,7 @@ __device__ __forceinline__ double priced_cost(double cost, double v, double coef
 struct SelSmem {
     RedSmem red;
     int bc_col, bc_neg;
+    double bq, bc0;
 };
 
 // Phase-2 pricing (simplex.ts:140-219, no optional objectives) in ONE pass over the cost row: the
@@ -251,18 +252,54 @@ struct SelSmem {
 // row as the staged pivot (rowsrc, q, coef0, cstar) WILL leave it (look-ahead); new_label = label of
 // column cstar after that pivot's swap; costsrc = the cost row to price (row 0 of the tableau, or a
 // scratch copy).  Result on every thread; *found = 0 when nothing prices in.
+// Per-thread pricing state: lowest batch index that holds a candidate of this thread's columns, and
+// the best (value, column) inside that batch.  Columns must be fed in increasing order.
+struct PriceAcc {
+    int myb, myneg;
+    VI x;
+};
+__device__ __forceinline__ void price_init(PriceAcc &a, double prec) {
+    a.myb = INT_MAX; a.myneg = 0; a.x.v = prec; a.x.i = INT_MAX;
+}
+// nc = (updated) reduced cost of column c, label = variable labelling it (only read for unrestricted models)
+__device__ __forceinline__ void price_consider(const TabDev &T, PriceAcc &a, int c, double nc, int label, int bsz) {
+    bool un = false;
+    if (T.unres != nullptr && nc < 0) un = is_unres(T, label);
+    const double v2 = un ? -nc : nc;
+    if (v2 > T.prec) {
+        const int b = (c - 1) / bsz;
+        if (b < a.myb) { a.myb = b; a.x.v = v2; a.x.i = c; a.myneg = un ? 1 : 0; }
+        else if (b == a.myb && v2 > a.x.v) { a.x.v = v2; a.x.i = c; a.myneg = un ? 1 : 0; }
+    }
+}
+// CTA-wide result: first batch with a candidate, arg-max inside it, lowest column on ties.
+__device__ __forceinline__ void price_finish(const TabDev &T, SelSmem &s, const PriceAcc &a, int *found_out, int *neg_out) {
+    const VI init = {T.prec, INT_MAX};
+    const int bstar = block_reduce_int<0>(a.myb, s.red);
+    int found = 0;
+    if (bstar != INT_MAX) {
+        const int mine = (a.myb == bstar) ? a.x.i : INT_MAX;
+        VI y = (a.myb == bstar) ? a.x : init;
+        y = block_reduce_vi<false>(y, init, s.red);
+        found = y.i;
+        if (mine == y.i) s.bc_neg = a.myneg;  // exactly one thread owns the winning column
+    }
+    __syncthreads();
+    *found_out = found;
+    *neg_out = found > 0 ? s.bc_neg : 0;
+    __syncthreads();
+}
+
 template <bool GLOBAL, bool PRICED>
 __device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *costsrc, const double *rowsrc, double q,
                                double coef0, int cstar, int new_label, int *found_out, int *neg_out) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int W = T.W;
-    const double prec = T.prec;
     const bool nzc = nz16(coef0);
     const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
-    int myb = INT_MAX, myneg = 0;
-    const VI init = {prec, INT_MAX};
-    VI x = init;
     const bool has_unres = T.unres != nullptr;
+    PriceAcc acc;
+    price_init(acc, T.prec);
     // all loads of a pass are issued before any data-dependent branch: one L2 round trip per 8*NT columns
     for (int c0 = 1; c0 < W; c0 += 8 * NT) {
         double cv[8], rv[8];
@@ -278,29 +315,12 @@ __device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *costsr
             if (c >= W) continue;
             double nc = cv[k];
             if (PRICED) nc = priced_cost(nc, rv[k], coef0, nzc, c == cstar, q);
-            bool un = false;
-            if (has_unres && nc < 0) un = is_unres(T, (PRICED && c == cstar) ? new_label : T.vcol[c]);
-            const double v2 = un ? -nc : nc;
-            if (v2 > prec) {
-                const int b = (c - 1) / bsz;
-                if (b < myb) { myb = b; x.v = v2; x.i = c; myneg = un ? 1 : 0; }
-                else if (b == myb && v2 > x.v) { x.v = v2; x.i = c; myneg = un ? 1 : 0; }
-            }
+            int label = -1;
+            if (has_unres && nc < 0) label = (PRICED && c == cstar) ? new_label : T.vcol[c];
+            price_consider(T, acc, c, nc, label, bsz);
         }
     }
-    const int bstar = block_reduce_int<0>(myb, s.red);
-    int found = 0;
-    if (bstar != INT_MAX) {
-        const int mine = (myb == bstar) ? x.i : INT_MAX;
-        VI y = (myb == bstar) ? x : init;
-        y = block_reduce_vi<false>(y, init, s.red);
-        found = y.i;
-        if (mine == y.i) s.bc_neg = myneg;  // exactly one thread owns the winning column
-    }
-    __syncthreads();
-    *found_out = found;
-    *neg_out = found > 0 ? s.bc_neg : 0;
-    __syncthreads();
+    price_finish(T, s, acc, found_out, neg_out);
 }
 
 // Literal, single-thread restatement of the pricing loop with optional objectives
@@ -372,7 +392,11 @@ __device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar,
     const int tid = threadIdx.x, NT = blockDim.x;
     const double *prowsrc = T.M + (size_t)rstar * T.stride;
     const double q = ldt<GLOBAL>(prowsrc + cstar);
-    const int leaving = T.vrow[rstar], entering = T.vcol[cstar];
+    int leaving = 0, entering = 0;
+    if (tid == 0) {  // only the thread that swaps the labels may read them (no barrier in between)
+        leaving = T.vrow[rstar];
+        entering = T.vcol[cstar];
+    }
     cta_copy_row<GLOBAL>(T.prow, prowsrc, T.W, T.stride);
     for (int o = tid; o < T.nOpt; o += NT) T.optcoef[o] = ldt<GLOBAL>(T.opt + (size_t)o * T.stride + cstar);
     if (tid == 0) {

@@ -362,32 +362,72 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
     const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
     const int leaving = T.vrow[rnext];
     const int entering = T.vcol[cn];
-    for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
-        double rv[8], cv[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c = c0 + tid + k * NT;
-            rv[k] = c < T.W ? ldg_cg(rowp + c) : 0.0;
-            cv[k] = c < T.W ? ldg_cg(src + c) : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c = c0 + tid + k * NT;
-            if (c >= T.stride) continue;
-            double ur = 0.0, uc = 0.0;
-            if (c < T.W) {
-                ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
-                uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
-            }
-            T.prow[c] = ur;
-            T.crow[c] = uc;
-        }
-    }
-    __syncthreads();
-    const double qn = ldg_cg(T.prow + cn);       // pivot element of the next pivot
-    const double coef0n = ldg_cg(T.crow + cn);   // its cost-row entry
     int found, neg;
-    cta_price_scan<true, true>(T, s, T.crow, T.prow, qn, coef0n, cn, leaving, &found, &neg);
+    double qn;
+    if (T.stride <= 8 * NT) {
+        // the whole row fits the CTA's registers (8 columns per thread): derive, stage and price
+        // without re-reading anything -- one L2 round trip for the two old rows
+        double ur[8], uc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = tid + k * NT;
+            ur[k] = c < T.W ? ldg_cg(rowp + c) : 0.0;
+            uc[k] = c < T.W ? ldg_cg(src + c) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = tid + k * NT;
+            if (c < T.W) {
+                ur[k] = new_entry(ur[k], is_prow, coef_r, frow[c], c == cstar, q);
+                uc[k] = new_entry(uc[k], false, coef0, frow[c], c == cstar, q);
+            }
+            if (c < T.stride) T.prow[c] = ur[k];
+            if (c == cn) { s.bq = ur[k]; s.bc0 = uc[k]; }  // pivot element / cost entry of the next pivot
+        }
+        __syncthreads();
+        qn = s.bq;
+        const double coef0n = s.bc0;
+        const bool nzc = nz16(coef0n);
+        const int bsz = T.use_partial ? T.batch_size : max(1, T.W - 1);
+        PriceAcc acc;
+        price_init(acc, T.prec);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = tid + k * NT;
+            if (c < 1 || c >= T.W) continue;
+            const double nc = priced_cost(uc[k], ur[k], coef0n, nzc, c == cn, qn);
+            int label = -1;
+            if (T.unres != nullptr && nc < 0) label = (c == cn) ? leaving : T.vcol[c];
+            price_consider(T, acc, c, nc, label, bsz);
+        }
+        price_finish(T, s, acc, &found, &neg);
+    } else {
+        for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
+            double rv[8], cv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = c0 + tid + k * NT;
+                rv[k] = c < T.W ? ldg_cg(rowp + c) : 0.0;
+                cv[k] = c < T.W ? ldg_cg(src + c) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = c0 + tid + k * NT;
+                if (c >= T.stride) continue;
+                double ur = 0.0, uc = 0.0;
+                if (c < T.W) {
+                    ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
+                    uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
+                }
+                T.prow[c] = ur;
+                T.crow[c] = uc;
+            }
+        }
+        __syncthreads();
+        qn = ldg_cg(T.prow + cn);                    // pivot element of the next pivot
+        const double coef0n = ldg_cg(T.crow + cn);   // its cost-row entry
+        cta_price_scan<true, true>(T, s, T.crow, T.prow, qn, coef0n, cn, leaving, &found, &neg);
+    }
     if (tid == 0) {
         if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rnext | (1 << 30), cn, leaving, entering);
         rec->log_n = log_n + 1;
@@ -466,24 +506,20 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             }
             s_coef[tid] = la_coef;
         }
-        mbar_wait(&bar, 0);
-        for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
-            const double v = frow[c];
-            double f = nz16(v) ? v / q : 0.0;
-            if (c == cstar) f = 1.0 / q;
-            if (flush && !nz16(f) && f != 0.0) f = 0.0;
-            frow[c] = f;
-        }
-        __syncthreads();
-        if (dbg && tid == 0) t1 = clock64();
-        if (b == G) {
-            cta_selector_pp(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after);
-            if (dbg && tid == 0) t2 = t3 = clock64();
-        } else {
+        if (b < G) {
+            // Publish the look-ahead partial first: it needs only two entries of the normalised pivot
+            // row, not the whole row, so it does not wait for the TMA copy -- the selector CTA can
+            // start choosing the next pivot ~2 us into the launch.
             if (want_partial) {  // ratio test of the NEXT pivot on this CTA's rows as this pivot leaves them
+                const double raw_n = ldg_cg(prow_arg + next_c), raw_0 = ldg_cg(prow_arg);
+                double f_n = nz16(raw_n) ? raw_n / q : 0.0;
+                if (next_c == cstar) f_n = 1.0 / q;
+                if (flush && !nz16(f_n) && f_n != 0.0) f_n = 0.0;
+                double f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
+                if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
                 const bool is_prow = (r0 + tid) == rstar;
-                const double col = new_entry(la_col, is_prow, la_coef, frow[next_c], next_c == cstar, q);
-                const double rhs = new_entry(la_rhs, is_prow, la_coef, frow[0], false, q);
+                const double col = new_entry(la_col, is_prow, la_coef, f_n, next_c == cstar, q);
+                const double rhs = new_entry(la_rhs, is_prow, la_coef, f_0, false, q);
                 const double prec = T.prec;
                 VI m = {INFINITY, INT_MAX};
                 int dmin = INT_MAX, cnt = 0;
@@ -504,11 +540,27 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                     p->minq = m.v; p->minr = m.i; p->dmin = dmin; p->cnt = cnt;
                 }
             }
-            if (tid == 0) {  // publish before streaming: the selector works while this CTA streams
+            if (tid == 0) {  // publish before streaming: the selector works while this CTA streams.
+                mbar_wait(&bar, 0);  // arrival also promises that this CTA no longer reads the prow buffer
                 __threadfence();
                 atomicAdd(&rec->arrive, 1u);
             }
             if (dbg && tid == 0) t2 = clock64();
+        }
+        mbar_wait(&bar, 0);
+        for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
+            const double v = frow[c];
+            double f = nz16(v) ? v / q : 0.0;
+            if (c == cstar) f = 1.0 / q;
+            if (flush && !nz16(f) && f != 0.0) f = 0.0;
+            frow[c] = f;
+        }
+        __syncthreads();
+        if (dbg && tid == 0) t1 = clock64();
+        if (b == G) {
+            cta_selector_pp(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after);
+            if (dbg && tid == 0) t2 = t3 = clock64();
+        } else {
             update_rows_pp<RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
             if (dbg && tid == 0) t3 = clock64();
         }

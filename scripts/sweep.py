@@ -32,8 +32,13 @@ def timeline(g, clock_ghz=1.965):
     g0 = buf[:, :, 0].astype(np.float64)
     start_spread = (g0.max(axis=1) - g0.min(axis=1)) / 1e3
     launch_period = np.diff(g0.min(axis=1)) / 1e3
+    sel_exit = float(done[last].mean()) if last.any() else None
+    rowm = ~last
     out = {
         "launches": int(buf.shape[0]), "grid": int(grid.value),
+        "t1_norm_us": float(staged[rowm].mean()), "t2_publish_us": float(rows[rowm].mean()),
+        "t3_rows_done_us": float(ticket[rowm].mean()), "t3_rows_done_max_us": float(ticket.max(axis=1).mean()),
+        "selector_exit_us": sel_exit,
         "stage_us_mean": float(staged.mean()), "stage_us_max": float(staged.max(axis=1).mean()),
         "rows_us_mean": float((rows - staged).mean()), "rows_us_max": float((rows - staged).max(axis=1).mean()),
         "to_ticket_us_mean": float(ticket.mean()), "to_ticket_us_max": float(ticket.max(axis=1).mean()),
