@@ -57,8 +57,9 @@ struct TabDev {
 
 // Look-ahead partial of one CTA: ratio test (simplex.ts:271-296) over its own freshly updated rows
 // against the NEXT entering column, so the last CTA only has to reduce gridDim.x of these.
-struct Part {
+struct __align__(16) Part {
     double minq;        // smallest admissible quotient among this CTA's rows (INF = none)
+    double pad0;        // keeps the four ints below on a 16-byte boundary (read as one int4)
     int minr;           // row of minq (INT_MAX = none)
     int dmin;           // first degenerate row (INT_MAX = none)
     int cnt;            // rows with a non-zero pivot-column entry (for the lazy flush flag)

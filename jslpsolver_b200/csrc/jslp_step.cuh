@@ -190,13 +190,27 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
     const VI init = {INFINITY, INT_MAX};
     VI m = init;
     int dmin = INT_MAX, cnt = 0;
-    const volatile Part *parts = T.part;
-    for (int b = tid; b < G; b += NT) {
-        const double pq = parts[b].minq;
-        const int pr = parts[b].minr, pd = parts[b].dmin;
-        cnt += parts[b].cnt;
-        if (pd < dmin) dmin = pd;
-        if (pr != INT_MAX && (pq < m.v || (pq == m.v && pr < m.i))) { m.v = pq; m.i = pr; }
+    const Part *parts = T.part;
+    for (int b0 = 0; b0 < G; b0 += 4 * NT) {  // all loads of a pass first: one L2 round trip
+        double pq[4];
+        int4 iv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = b0 + tid + k * NT;
+            if (b < G) {
+                pq[k] = __ldcg(&parts[b].minq);
+                iv[k] = __ldcg(reinterpret_cast<const int4 *>(&parts[b].minr));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = b0 + tid + k * NT;
+            if (b >= G) continue;
+            const int pr = iv[k].x, pd = iv[k].y;
+            cnt += iv[k].z;
+            if (pd < dmin) dmin = pd;
+            if (pr != INT_MAX && (pq[k] < m.v || (pq[k] == m.v && pr < m.i))) { m.v = pq[k]; m.i = pr; }
+        }
     }
     block_reduce_ratio(dmin, m, cnt, s.red);
     const int dall = dmin;
@@ -293,7 +307,7 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
 // The selector CTA of a ping-pong step.  frow = normalised pivot row of the pivot being executed.
 __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
                                 int rstar, int cstar, double q, int cn, int isneg, int launch, int p2, int log_n,
-                                bool stop_after) {
+                                bool stop_after, long long *ts) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const double *src = T.M;
     // wait until every row CTA has published its partial (bounded spin: a lost arrival must not hang the GPU)
@@ -313,6 +327,7 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
         return;
     }
     __threadfence();
+    if (tid == 0) ts[0] = clock64();
     const double coef0 = ldg_cg(src + cstar);  // cost-row entry of the executing pivot's column
     auto flip = [&]() {  // the updated tableau becomes the current one
         Tp->M = T.M2;
@@ -333,15 +348,30 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
     const VI init = {INFINITY, INT_MAX};
     VI m = init;
     int dmin = INT_MAX, cnt = 0;
-    const volatile Part *parts = T.part;
-    for (int b = tid; b < G; b += NT) {
-        const double pq = parts[b].minq;
-        const int pr = parts[b].minr, pd = parts[b].dmin;
-        cnt += parts[b].cnt;
-        if (pd < dmin) dmin = pd;
-        if (pr != INT_MAX && (pq < m.v || (pq == m.v && pr < m.i))) { m.v = pq; m.i = pr; }
+    const Part *parts = T.part;
+    for (int b0 = 0; b0 < G; b0 += 4 * NT) {  // all loads of a pass first: one L2 round trip
+        double pq[4];
+        int4 iv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = b0 + tid + k * NT;
+            if (b < G) {
+                pq[k] = __ldcg(&parts[b].minq);
+                iv[k] = __ldcg(reinterpret_cast<const int4 *>(&parts[b].minr));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = b0 + tid + k * NT;
+            if (b >= G) continue;
+            const int pr = iv[k].x, pd = iv[k].y;
+            cnt += iv[k].z;
+            if (pd < dmin) dmin = pd;
+            if (pr != INT_MAX && (pq[k] < m.v || (pq[k] == m.v && pr < m.i))) { m.v = pq[k]; m.i = pr; }
+        }
     }
     block_reduce_ratio(dmin, m, cnt, s.red);
+    if (tid == 0) ts[1] = clock64();
     int rnext;
     if (dmin != INT_MAX) rnext = dmin;
     else if (m.i != INT_MAX) rnext = m.i;
@@ -385,6 +415,7 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
             if (c == cn) { s.bq = ur[k]; s.bc0 = uc[k]; }  // pivot element / cost entry of the next pivot
         }
         __syncthreads();
+        if (tid == 0) ts[2] = clock64();
         qn = s.bq;
         const double coef0n = s.bc0;
         const bool nzc = nz16(coef0n);
@@ -558,8 +589,11 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         __syncthreads();
         if (dbg && tid == 0) t1 = clock64();
         if (b == G) {
-            cta_selector_pp(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after);
-            if (dbg && tid == 0) t2 = t3 = clock64();
+            long long ts[3] = {0, 0, 0};
+            cta_selector_pp(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after, ts);
+            if (dbg && tid == 0) {  // selector record: arrivals seen, partials reduced, rows derived, exit
+                t2 = ts[0]; t3 = ts[1]; g0 = ts[2] - t0;
+            }
         } else {
             update_rows_pp<RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
             if (dbg && tid == 0) t3 = clock64();
@@ -569,7 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             unsigned int smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             long long *d = T.dbg + ((size_t)launch * T.dbg_grid + b) * 8;
-            d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = (b == G); d[7] = nr;
+            d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = (b == G); d[7] = nr;  // selector: d[0] = cycles to rows-derived
         }
         return;
     }

@@ -30,15 +30,23 @@ def timeline(g, clock_ghz=1.965):
     staged, rows, ticket, done = (us(buf[:, :, k].astype(np.float64)) for k in (1, 2, 3, 4))
     last = buf[:, :, 6] == 1
     g0 = buf[:, :, 0].astype(np.float64)
-    start_spread = (g0.max(axis=1) - g0.min(axis=1)) / 1e3
-    launch_period = np.diff(g0.min(axis=1)) / 1e3
+    g0 = np.where(g0 > 1e12, g0, np.nan)  # globaltimer stamps only (the selector's slot 0 holds a cycle count)
+    start_spread = (np.nanmax(g0, axis=1) - np.nanmin(g0, axis=1)) / 1e3
+    launch_period = np.diff(np.nanmin(g0, axis=1)) / 1e3
     sel_exit = float(done[last].mean()) if last.any() else None
     rowm = ~last
+    sel = {}
+    if last.any():  # selector record: d1 norm, d2 arrivals seen, d3 partials reduced, d0 rows derived, d4 exit
+        sel = {"sel_norm": float(staged[last].mean()), "sel_arrivals_seen": float(rows[last].mean()),
+               "sel_partials_reduced": float(ticket[last].mean()),
+               "sel_rows_derived": float(us(buf[:, :, 0].astype(np.float64))[last].mean()),
+               "sel_exit": sel_exit,
+               "last_publish_us": float(np.where(rowm, rows, 0).max(axis=1).mean())}
     out = {
         "launches": int(buf.shape[0]), "grid": int(grid.value),
         "t1_norm_us": float(staged[rowm].mean()), "t2_publish_us": float(rows[rowm].mean()),
         "t3_rows_done_us": float(ticket[rowm].mean()), "t3_rows_done_max_us": float(ticket.max(axis=1).mean()),
-        "selector_exit_us": sel_exit,
+        "selector_exit_us": sel_exit, "selector": sel,
         "stage_us_mean": float(staged.mean()), "stage_us_max": float(staged.max(axis=1).mean()),
         "rows_us_mean": float((rows - staged).mean()), "rows_us_max": float((rows - staged).max(axis=1).mean()),
         "to_ticket_us_mean": float(ticket.mean()), "to_ticket_us_max": float(ticket.max(axis=1).mean()),
