@@ -468,8 +468,8 @@ static int build_graphs(jslp_tab *t) {
     cudaStream_t s = t->ctx->stream;
     const StepVariant &sv = step_variant(t);
     CK(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // 2 = ping-pong step: the last CTA of the grid is the selector (needs at least one row CTA besides it)
-    const int fused_mode = (t->pingpong && t->lookahead && grid >= 2) ? 2 : 1;
+    // 2 = ping-pong step: the last two CTAs of the grid are the selectors (at least one row CTA besides them)
+    const int fused_mode = (t->pingpong && t->lookahead && grid >= 3) ? 2 : 1;
     for (int mode = 0; mode < 4; mode++) {  // {fused, two-kernel} x {long batch, short first batch}
         const int nsteps = mode >= 2 ? SMALL_BATCH : t->batch;
         cudaGraph_t g;
@@ -742,6 +742,8 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     *t->h_rec = init;
     if (timed) CK(cudaEventRecord(ctx->ev0, s));
     CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));
+    // look-ahead partial slots: no stale message may carry a sequence tag of this solve
+    if (t->hd.part) CK(cudaMemsetAsync(t->hd.part, 0xff, sizeof(Part) * (size_t)t->part_cap, s));
     CK(cudaStreamSynchronize(s));  // h_rec is reused as the read-back buffer below
 
     if (only_phase != 2) t->bounded = 1;  // simplex.ts:15
@@ -811,6 +813,7 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             // a pivot pending in the snapshot was selected in an earlier batch, hence done < hit_at.
             r.stop_at = (int)hit_at;
             t->h_rec[slot] = r;
+            if (t->hd.part) CK(cudaMemsetAsync(t->hd.part, 0xff, sizeof(Part) * (size_t)t->part_cap, s));
             CK(cudaMemcpyAsync(t->d_rec, t->h_rec + slot, sizeof(Rec), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
             CK(cudaGraphLaunch(graphs[kind_of[slot]], s));

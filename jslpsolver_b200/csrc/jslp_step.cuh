@@ -304,30 +304,75 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
     }
 }
 
-// The selector CTA of a ping-pong step.  frow = normalised pivot row of the pivot being executed.
-__device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
-                                int rstar, int cstar, double q, int cn, int isneg, int launch, int p2, int log_n,
-                                bool stop_after, long long *ts) {
+// ---- look-ahead partials as self-validating 16-byte messages -------------------------------------
+// A row CTA publishes the ratio-test partial of its rows with ONE 128-bit store; selectors poll the
+// slots.  Word B carries a 24-bit sequence tag (launch + 1) and a 16-bit checksum of word A, so a
+// reader accepts a slot only when both halves belong to the same publication: no fence, no atomic,
+// no barrier on the publishing side.  Rows are encoded relative to the CTA's first row (<= 254 rows).
+__device__ __forceinline__ unsigned int part_chk(unsigned long long a, unsigned int seq) {
+    const unsigned long long x = a ^ (a >> 16) ^ (a >> 32) ^ (a >> 48);
+    return (unsigned int)((x ^ seq ^ (seq >> 16)) & 0xffffull);
+}
+__device__ __forceinline__ void part_publish(Part *slot, double minq, int minr_rel, int dmin_rel, int cnt, unsigned int seq) {
+    const unsigned long long a = (unsigned long long)__double_as_longlong(minq);
+    const unsigned long long b = (unsigned long long)(seq & 0xffffffu) | ((unsigned long long)(cnt & 0xff) << 24) |
+                                 ((unsigned long long)(minr_rel & 0xff) << 32) | ((unsigned long long)(dmin_rel & 0xff) << 40) |
+                                 ((unsigned long long)part_chk(a, seq & 0xffffffu) << 48);
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(a), "l"(b) : "memory");
+}
+// returns true when the slot holds the publication tagged `seq`
+__device__ __forceinline__ bool part_try_read(const Part *slot, unsigned int seq, double *minq, int *minr_rel,
+                                              int *dmin_rel, int *cnt) {
+    unsigned long long a, b;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(slot) : "memory");
+    if ((unsigned int)(b & 0xffffffull) != (seq & 0xffffffu)) return false;
+    if ((unsigned int)(b >> 48) != part_chk(a, seq & 0xffffffu)) return false;
+    *minq = __longlong_as_double((long long)a);
+    *cnt = (int)((b >> 24) & 0xff);
+    *minr_rel = (int)((b >> 32) & 0xff);
+    *dmin_rel = (int)((b >> 40) & 0xff);
+    return true;
+}
+
+// Selector side: wait for all G partials of this launch and reduce them (simplex.ts:271-296 over the
+// whole column).  Returns false on a watchdog timeout (a lost publication must not hang the GPU).
+__device__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigned int seq, int *rnext, int *cnt_out) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int base = T.H / G, rem = T.H % G;
+    VI m = {INFINITY, INT_MAX};
+    int dmin = INT_MAX, cnt = 0, ok = 1;
+    const long long tstart = clock64();
+    for (int b = tid; b < G; b += NT) {
+        const int r0 = b * base + min(b, rem);
+        double pq;
+        int mr, dr, pc;
+        while (!part_try_read(T.part + b, seq, &pq, &mr, &dr, &pc)) {
+            __nanosleep(20);
+            if (clock64() - tstart > 4000000000LL) { ok = 0; break; }
+        }
+        if (!ok) break;
+        cnt += pc;
+        if (dr != 255 && r0 + dr < dmin) dmin = r0 + dr;
+        if (mr != 255) {
+            const int pr = r0 + mr;
+            if (pq < m.v || (pq == m.v && pr < m.i)) { m.v = pq; m.i = pr; }
+        }
+    }
+    ok = block_reduce_int<0>(ok, s.red);
+    if (!ok) return false;
+    block_reduce_ratio(dmin, m, cnt, s.red);
+    *rnext = dmin != INT_MAX ? dmin : (m.i != INT_MAX ? m.i : -1);
+    *cnt_out = cnt;
+    return true;
+}
+
+// Selector S1 of a ping-pong step: decides the next pivot, prices the one after it, writes the
+// record, swaps the labels and flips the descriptor.  frow = normalised row of the executing pivot.
+__device__ void cta_selector_decide(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
+                                    int rstar, int cstar, double q, int cn, int isneg, int launch, int p2, int log_n,
+                                    bool stop_after, long long *ts) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const double *src = T.M;
-    // wait until every row CTA has published its partial (bounded spin: a lost arrival must not hang the GPU)
-    if (tid == 0) {
-        const long long tstart = clock64();
-        volatile unsigned int *arr = &rec->arrive;
-        bool ok = true;
-        while (*arr < (unsigned int)G) {
-            __nanosleep(40);
-            if (clock64() - tstart > 4000000000LL) { ok = false; break; }
-        }
-        s.bc_col = ok ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s.bc_col) {
-        if (tid == 0) { rec->status = ST_ERROR; rec->has_pivot = 0; rec->arrive = 0; }
-        return;
-    }
-    __threadfence();
-    if (tid == 0) ts[0] = clock64();
     const double coef0 = ldg_cg(src + cstar);  // cost-row entry of the executing pivot's column
     auto flip = [&]() {  // the updated tableau becomes the current one
         Tp->M = T.M2;
@@ -335,7 +380,6 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
     };
     if (cn == 0 || stop_after) {  // optimal after this pivot (simplex.ts:265-269), or a replay stop
         if (tid == 0) {
-            rec->arrive = 0;
             rec->done = launch + 1; rec->p2 = p2 + 1; rec->has_pivot = 0;
             if (!stop_after) {
                 rec->status = ST_OPTIMAL; rec->phase = 2;
@@ -345,39 +389,14 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
         }
         return;
     }
-    const VI init = {INFINITY, INT_MAX};
-    VI m = init;
-    int dmin = INT_MAX, cnt = 0;
-    const Part *parts = T.part;
-    for (int b0 = 0; b0 < G; b0 += 4 * NT) {  // all loads of a pass first: one L2 round trip
-        double pq[4];
-        int4 iv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int b = b0 + tid + k * NT;
-            if (b < G) {
-                pq[k] = __ldcg(&parts[b].minq);
-                iv[k] = __ldcg(reinterpret_cast<const int4 *>(&parts[b].minr));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int b = b0 + tid + k * NT;
-            if (b >= G) continue;
-            const int pr = iv[k].x, pd = iv[k].y;
-            cnt += iv[k].z;
-            if (pd < dmin) dmin = pd;
-            if (pr != INT_MAX && (pq[k] < m.v || (pq[k] == m.v && pr < m.i))) { m.v = pq[k]; m.i = pr; }
-        }
+    int rnext, cnt;
+    if (!cta_collect_partials(T, s, G, (unsigned int)(launch + 1), &rnext, &cnt)) {
+        if (tid == 0) { rec->status = ST_ERROR; rec->has_pivot = 0; }
+        return;
     }
-    block_reduce_ratio(dmin, m, cnt, s.red);
-    if (tid == 0) ts[1] = clock64();
-    int rnext;
-    if (dmin != INT_MAX) rnext = dmin;
-    else if (m.i != INT_MAX) rnext = m.i;
-    else {  // unbounded (simplex.ts:298-303)
+    if (tid == 0) ts[0] = ts[1] = clock64();
+    if (rnext < 0) {  // unbounded (simplex.ts:298-303)
         if (tid == 0) {
-            rec->arrive = 0;
             rec->done = launch + 1; rec->p2 = p2 + 1; rec->has_pivot = 0;
             rec->status = ST_UNBOUNDED; rec->phase = 2;
             rec->unbounded_var = T.vcol[cn];
@@ -386,54 +405,44 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
         }
         return;
     }
-    // next pivot row and cost row as the executing pivot leaves them, from the old tableau
+    // Entries of the next pivot row / the cost row as the executing pivot leaves them, derived from
+    // the OLD tableau.  First pass: only the leading columns (one per thread) -- the reference's
+    // partial pricing almost always stops in the first batches.
     const double *rowp = src + (size_t)rnext * T.stride;
     const bool is_prow = rnext == rstar;
     const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
     const int leaving = T.vrow[rnext];
     const int entering = T.vcol[cn];
-    int found, neg;
-    double qn;
-    if (T.stride <= 8 * NT) {
-        // the whole row fits the CTA's registers (8 columns per thread): derive, stage and price
-        // without re-reading anything -- one L2 round trip for the two old rows
-        double ur[8], uc[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c = tid + k * NT;
-            ur[k] = c < T.W ? ldg_cg(rowp + c) : 0.0;
-            uc[k] = c < T.W ? ldg_cg(src + c) : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c = tid + k * NT;
-            if (c < T.W) {
-                ur[k] = new_entry(ur[k], is_prow, coef_r, frow[c], c == cstar, q);
-                uc[k] = new_entry(uc[k], false, coef0, frow[c], c == cstar, q);
-            }
-            if (c < T.stride) T.prow[c] = ur[k];
-            if (c == cn) { s.bq = ur[k]; s.bc0 = uc[k]; }  // pivot element / cost entry of the next pivot
-        }
-        __syncthreads();
-        if (tid == 0) ts[2] = clock64();
-        qn = s.bq;
-        const double coef0n = s.bc0;
-        const bool nzc = nz16(coef0n);
-        const int bsz = T.use_partial ? T.batch_size : max(1, T.W - 1);
+    const double rv_cn = ldg_cg(rowp + cn), cv_cn = ldg_cg(src + cn);
+    const int c1 = tid;  // column of the first pass
+    double rv1 = 0.0, cv1 = 0.0;
+    if (c1 >= 1 && c1 < T.W) { rv1 = ldg_cg(rowp + c1); cv1 = ldg_cg(src + c1); }
+    const double qn = new_entry(rv_cn, is_prow, coef_r, frow[cn], cn == cstar, q);      // next pivot element
+    const double coef0n = new_entry(cv_cn, false, coef0, frow[cn], cn == cstar, q);     // its cost-row entry
+    const bool nzc = nz16(coef0n);
+    const int bsz = T.use_partial ? T.batch_size : max(1, T.W - 1);
+    // batches that lie entirely inside the first pass (columns 1 .. NT-1)
+    const int covered = min(T.W - 1, NT - 1);
+    const int nfull = (covered == T.W - 1) ? INT_MAX : covered / bsz;
+    int found = 0, neg = 0;
+    {
         PriceAcc acc;
         price_init(acc, T.prec);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c = tid + k * NT;
-            if (c < 1 || c >= T.W) continue;
-            const double nc = priced_cost(uc[k], ur[k], coef0n, nzc, c == cn, qn);
+        if (c1 >= 1 && c1 < T.W && (c1 - 1) / bsz < nfull) {
+            const double ur = new_entry(rv1, is_prow, coef_r, frow[c1], c1 == cstar, q);
+            const double uc = new_entry(cv1, false, coef0, frow[c1], c1 == cstar, q);
+            const double nc = priced_cost(uc, ur, coef0n, nzc, c1 == cn, qn);
             int label = -1;
-            if (T.unres != nullptr && nc < 0) label = (c == cn) ? leaving : T.vcol[c];
-            price_consider(T, acc, c, nc, label, bsz);
+            if (T.unres != nullptr && nc < 0) label = (c1 == cn) ? leaving : T.vcol[c1];
+            price_consider(T, acc, c1, nc, label, bsz);
         }
         price_finish(T, s, acc, &found, &neg);
-    } else {
-        for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
+    }
+    if (tid == 0) ts[2] = clock64();
+    if (found == 0 && nfull != INT_MAX) {  // nothing in the leading batches: price the whole row
+        PriceAcc acc;
+        price_init(acc, T.prec);
+        for (int c0 = 1; c0 < T.W; c0 += 8 * NT) {
             double rv[8], cv[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -444,27 +453,22 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int c = c0 + tid + k * NT;
-                if (c >= T.stride) continue;
-                double ur = 0.0, uc = 0.0;
-                if (c < T.W) {
-                    ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
-                    uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
-                }
-                T.prow[c] = ur;
-                T.crow[c] = uc;
+                if (c >= T.W) continue;
+                const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
+                const double uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
+                const double nc = priced_cost(uc, ur, coef0n, nzc, c == cn, qn);
+                int label = -1;
+                if (T.unres != nullptr && nc < 0) label = (c == cn) ? leaving : T.vcol[c];
+                price_consider(T, acc, c, nc, label, bsz);
             }
         }
-        __syncthreads();
-        qn = ldg_cg(T.prow + cn);                    // pivot element of the next pivot
-        const double coef0n = ldg_cg(T.crow + cn);   // its cost-row entry
-        cta_price_scan<true, true>(T, s, T.crow, T.prow, qn, coef0n, cn, leaving, &found, &neg);
+        price_finish(T, s, acc, &found, &neg);
     }
     if (tid == 0) {
         if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rnext | (1 << 30), cn, leaving, entering);
         rec->log_n = log_n + 1;
         T.vrow[rnext] = entering;  // simplex.ts:339-349
         T.vcol[cn] = leaving;
-        rec->arrive = 0;
         rec->done = launch + 1; rec->p2 = p2 + 1;
         rec->phase = 2; rec->r = rnext; rec->c = cn; rec->q = qn; rec->is_neg = isneg;
         rec->flush = (cnt - (nz16(qn) ? 1 : 0)) > 0;
@@ -474,10 +478,40 @@ __device__ void cta_selector_pp(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &
     }
 }
 
+// Selector S2 of a ping-pong step: stages the raw pivot row of the next pivot (the row as the
+// executing pivot leaves it) into the prow side buffer, the TMA source of the next launch.
+__device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G, int rstar,
+                                   int cstar, double q, int cn, int launch, bool stop_after) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    if (cn == 0 || stop_after) return;
+    int rnext, cnt;
+    if (!cta_collect_partials(T, s, G, (unsigned int)(launch + 1), &rnext, &cnt)) return;  // S1 reports the error
+    if (rnext < 0) return;
+    const double *src = T.M;
+    const double *rowp = src + (size_t)rnext * T.stride;
+    const bool is_prow = rnext == rstar;
+    const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
+    for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
+        double rv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            rv[k] = c < T.W ? ldg_cg(rowp + c) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            if (c >= T.stride) continue;
+            T.prow[c] = c < T.W ? new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q) : 0.0;
+        }
+    }
+    (void)rec;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 // do_select: 0 = update only (two-kernel engine), 1 = the last CTA selects the next pivot,
-// 2 = ping-pong: the grid carries one extra CTA (the selector); steps that are not eligible for the
-// ping-pong path (phase 1, bootstrap, optional objectives) run in place on the first gridDim.x-1 CTAs.
+// 2 = ping-pong: the grid carries two extra CTAs (the selectors); steps that are not eligible for the
+// ping-pong path (phase 1, bootstrap, optional objectives) run in place on the first gridDim.x-2 CTAs.
 // prow_arg / stride_arg duplicate TabDev.prow / stride (both immutable after jslp_tab_create) so the
 // TMA copy of the pivot row can be issued before the descriptor has been fetched.
 template <int NTHREADS, int MINB, int RC, bool PF>
@@ -488,7 +522,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     __shared__ SelSmem sel;
     __shared__ uint64_t bar;
     __shared__ int s_last;
-    __shared__ double s_coef[NTHREADS];
+    __shared__ double s_coef[32];
+    __shared__ long long s_t0;
     const int tid = threadIdx.x, NT = blockDim.x;
     // Programmatic dependent launch: let the next step's CTAs be scheduled while this grid drains,
     // and do not touch anything the previous step wrote before it has completed.  Both are no-ops
@@ -501,6 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, g0 = 0;
     if (tid == 0) {
         t0 = clock64();
+        s_t0 = t0;
         mbar_init(&bar, 1);
         fence_mbar_init();
         mbar_expect_tx(&bar, (uint32_t)stride_arg * 8u);
@@ -517,66 +553,31 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     if (dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
 
     const int b = blockIdx.x;
-    const int G = do_select == 2 ? (int)gridDim.x - 1 : (int)gridDim.x;  // row CTAs
+    const int G = do_select == 2 ? (int)gridDim.x - 2 : (int)gridDim.x;  // row CTAs (ping-pong: + 2 selector CTAs)
     const int base = T.H / G, rem = T.H % G;
     const int r0 = b * base + min(b, rem);
     const int nr = b < G ? base + (b < rem ? 1 : 0) : 0;
     const bool rows_fit = base + 1 <= NT;  // one row per thread in the look-ahead (uniform over the grid)
 
     // ------------------------------------------------------------------ ping-pong path
-    const bool pp = do_select == 2 && next_c >= 0 && phase == 2 && T.nOpt == 0 && T.M2 != nullptr && rows_fit;
+    // Grid = G row CTAs + 2 selector CTAs (decide, stage).  Eligible: phase 2 with the next entering
+    // column already priced, no optional objectives, at most 32 rows per CTA (one warp runs the
+    // look-ahead ratio test of the CTA's rows).
+    const bool pp = do_select == 2 && next_c >= 0 && phase == 2 && T.nOpt == 0 && T.M2 != nullptr && base + 1 <= 32;
     if (pp) {
         const bool want_partial = next_c > 0 && !stop_after;
+        const int lw = (NT >> 5) - 1;           // the warp that runs the look-ahead (last warp)
+        const int lane = tid & 31;
+        const bool la_warp = (tid >> 5) == lw && b < G;
         double la_col = 0.0, la_rhs = 0.0, la_coef = 0.0;
-        if (tid < nr) {  // this thread's row: pivot-column entry, and the look-ahead operands
-            const size_t off = (size_t)(r0 + tid) * T.stride;
+        if (la_warp && lane < nr) {  // this lane's row: pivot-column entry and the look-ahead operands
+            const size_t off = (size_t)(r0 + lane) * T.stride;
             la_coef = ldg_cg(T.M + off + cstar);
             if (want_partial) {
                 la_col = ldg_cg(T.M + off + next_c);
                 la_rhs = ldg_cg(T.M + off);
             }
-            s_coef[tid] = la_coef;
-        }
-        if (b < G) {
-            // Publish the look-ahead partial first: it needs only two entries of the normalised pivot
-            // row, not the whole row, so it does not wait for the TMA copy -- the selector CTA can
-            // start choosing the next pivot ~2 us into the launch.
-            if (want_partial) {  // ratio test of the NEXT pivot on this CTA's rows as this pivot leaves them
-                const double raw_n = ldg_cg(prow_arg + next_c), raw_0 = ldg_cg(prow_arg);
-                double f_n = nz16(raw_n) ? raw_n / q : 0.0;
-                if (next_c == cstar) f_n = 1.0 / q;
-                if (flush && !nz16(f_n) && f_n != 0.0) f_n = 0.0;
-                double f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
-                if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
-                const bool is_prow = (r0 + tid) == rstar;
-                const double col = new_entry(la_col, is_prow, la_coef, f_n, next_c == cstar, q);
-                const double rhs = new_entry(la_rhs, is_prow, la_coef, f_0, false, q);
-                const double prec = T.prec;
-                VI m = {INFINITY, INT_MAX};
-                int dmin = INT_MAX, cnt = 0;
-                if (tid < nr) {
-                    const int r = r0 + tid;
-                    if (nz16(col)) cnt = 1;
-                    if (r != 0 && !(-prec < col && col < prec)) {
-                        if (col > 0 && prec > rhs && rhs > -prec) dmin = r;
-                        else {
-                            const double quo = next_neg ? -rhs / col : rhs / col;
-                            if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
-                        }
-                    }
-                }
-                block_reduce_ratio(dmin, m, cnt, sel.red);
-                if (tid == 0) {
-                    Part *p = T.part + b;
-                    p->minq = m.v; p->minr = m.i; p->dmin = dmin; p->cnt = cnt;
-                }
-            }
-            if (tid == 0) {  // publish before streaming: the selector works while this CTA streams.
-                mbar_wait(&bar, 0);  // arrival also promises that this CTA no longer reads the prow buffer
-                __threadfence();
-                atomicAdd(&rec->arrive, 1u);
-            }
-            if (dbg && tid == 0) t2 = clock64();
+            s_coef[lane] = la_coef;
         }
         mbar_wait(&bar, 0);
         for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
@@ -590,11 +591,47 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         if (dbg && tid == 0) t1 = clock64();
         if (b == G) {
             long long ts[3] = {0, 0, 0};
-            cta_selector_pp(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after, ts);
-            if (dbg && tid == 0) {  // selector record: arrivals seen, partials reduced, rows derived, exit
-                t2 = ts[0]; t3 = ts[1]; g0 = ts[2] - t0;
-            }
+            cta_selector_decide(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after, ts);
+            if (dbg && tid == 0) { t2 = ts[0]; t3 = ts[1]; g0 = ts[2] - t0; }  // partials in, reduced, first pricing pass
+        } else if (b == G + 1) {
+            cta_selector_stage(T, rec, sel, frow, G, rstar, cstar, q, next_c, launch, stop_after);
+            if (dbg && tid == 0) t2 = t3 = clock64();
         } else {
+            if (la_warp && want_partial) {
+                // ratio test of the NEXT pivot on this CTA's rows as this pivot leaves them (one warp,
+                // shuffles only), published as one 16-byte message; the other warps are already streaming
+                const bool is_prow = (r0 + lane) == rstar;
+                const double col = new_entry(la_col, is_prow, la_coef, frow[next_c], next_c == cstar, q);
+                const double rhs = new_entry(la_rhs, is_prow, la_coef, frow[0], false, q);
+                const double prec = T.prec;
+                VI m = {INFINITY, INT_MAX};
+                int dmin = INT_MAX, cnt = 0;
+                if (lane < nr) {
+                    const int r = r0 + lane;
+                    if (nz16(col)) cnt = 1;
+                    if (r != 0 && !(-prec < col && col < prec)) {
+                        if (col > 0 && prec > rhs && rhs > -prec) dmin = lane;
+                        else {
+                            const double quo = next_neg ? -rhs / col : rhs / col;
+                            if (quo > prec && m.v > quo) { m.v = quo; m.i = lane; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    VI y;
+                    y.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+                    y.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+                    if (better<true>(y, m)) m = y;
+                    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                }
+                if (lane == 0)
+                    part_publish(T.part + b, m.v, m.i == INT_MAX ? 255 : m.i, dmin == INT_MAX ? 255 : dmin, cnt,
+                                 (unsigned int)(launch + 1));
+            }
+            if (dbg && tid == NT - 32)  // publish time of the look-ahead warp
+                T.dbg[((size_t)launch * T.dbg_grid + b) * 8 + 2] = clock64() - s_t0;
             update_rows_pp<RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
             if (dbg && tid == 0) t3 = clock64();
         }
@@ -603,7 +640,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             unsigned int smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             long long *d = T.dbg + ((size_t)launch * T.dbg_grid + b) * 8;
-            d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = (b == G); d[7] = nr;  // selector: d[0] = cycles to rows-derived
+            d[0] = g0; d[1] = t1 - t0; if (b >= G) d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid;
+            d[6] = (b == G) ? 1 : (b == G + 1 ? 2 : 0); d[7] = nr;
         }
         return;
     }
