@@ -342,20 +342,37 @@ __device__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigne
     VI m = {INFINITY, INT_MAX};
     int dmin = INT_MAX, cnt = 0, ok = 1;
     const long long tstart = clock64();
-    for (int b = tid; b < G; b += NT) {
-        const int r0 = b * base + min(b, rem);
-        double pq;
-        int mr, dr, pc;
-        while (!part_try_read(T.part + b, seq, &pq, &mr, &dr, &pc)) {
-            __nanosleep(20);
-            if (clock64() - tstart > 4000000000LL) { ok = 0; break; }
-        }
-        if (!ok) break;
-        cnt += pc;
-        if (dr != 255 && r0 + dr < dmin) dmin = r0 + dr;
-        if (mr != 255) {
-            const int pr = r0 + mr;
-            if (pq < m.v || (pq == m.v && pr < m.i)) { m.v = pq; m.i = pr; }
+    for (int b0 = 0; b0 < G && ok; b0 += 4 * NT) {  // up to four slots per thread are polled together
+        unsigned int pending = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (b0 + tid + k * NT < G) pending |= 1u << k;
+        while (pending) {
+            double pq[4];
+            int mr[4], dr[4], pc[4];
+            bool got[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                got[k] = false;
+                if (pending & (1u << k)) got[k] = part_try_read(T.part + b0 + tid + k * NT, seq, &pq[k], &mr[k], &dr[k], &pc[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!got[k]) continue;
+                pending &= ~(1u << k);
+                const int b = b0 + tid + k * NT;
+                const int r0 = b * base + min(b, rem);
+                cnt += pc[k];
+                if (dr[k] != 255 && r0 + dr[k] < dmin) dmin = r0 + dr[k];
+                if (mr[k] != 255) {
+                    const int pr = r0 + mr[k];
+                    if (pq[k] < m.v || (pq[k] == m.v && pr < m.i)) { m.v = pq[k]; m.i = pr; }
+                }
+            }
+            if (pending) {
+                __nanosleep(20);
+                if (clock64() - tstart > 4000000000LL) { ok = 0; break; }
+            }
         }
     }
     ok = block_reduce_int<0>(ok, s.red);
@@ -414,27 +431,36 @@ __device__ void cta_selector_decide(TabDev *Tp, const TabDev &T, Rec *rec, SelSm
     const int leaving = T.vrow[rnext];
     const int entering = T.vcol[cn];
     const double rv_cn = ldg_cg(rowp + cn), cv_cn = ldg_cg(src + cn);
-    const int c1 = tid;  // column of the first pass
-    double rv1 = 0.0, cv1 = 0.0;
-    if (c1 >= 1 && c1 < T.W) { rv1 = ldg_cg(rowp + c1); cv1 = ldg_cg(src + c1); }
+    constexpr int K1 = 4;  // columns per thread in the first pass (c = tid + k*NT)
+    double rv1[K1], cv1[K1];
+#pragma unroll
+    for (int k = 0; k < K1; k++) {
+        const int c = tid + k * NT;
+        rv1[k] = (c >= 1 && c < T.W) ? ldg_cg(rowp + c) : 0.0;
+        cv1[k] = (c >= 1 && c < T.W) ? ldg_cg(src + c) : 0.0;
+    }
     const double qn = new_entry(rv_cn, is_prow, coef_r, frow[cn], cn == cstar, q);      // next pivot element
     const double coef0n = new_entry(cv_cn, false, coef0, frow[cn], cn == cstar, q);     // its cost-row entry
     const bool nzc = nz16(coef0n);
     const int bsz = T.use_partial ? T.batch_size : max(1, T.W - 1);
-    // batches that lie entirely inside the first pass (columns 1 .. NT-1)
-    const int covered = min(T.W - 1, NT - 1);
+    // batches that lie entirely inside the first pass (columns 1 .. K1*NT-1)
+    const int covered = min(T.W - 1, K1 * NT - 1);
     const int nfull = (covered == T.W - 1) ? INT_MAX : covered / bsz;
     int found = 0, neg = 0;
     {
         PriceAcc acc;
         price_init(acc, T.prec);
-        if (c1 >= 1 && c1 < T.W && (c1 - 1) / bsz < nfull) {
-            const double ur = new_entry(rv1, is_prow, coef_r, frow[c1], c1 == cstar, q);
-            const double uc = new_entry(cv1, false, coef0, frow[c1], c1 == cstar, q);
-            const double nc = priced_cost(uc, ur, coef0n, nzc, c1 == cn, qn);
-            int label = -1;
-            if (T.unres != nullptr && nc < 0) label = (c1 == cn) ? leaving : T.vcol[c1];
-            price_consider(T, acc, c1, nc, label, bsz);
+#pragma unroll
+        for (int k = 0; k < K1; k++) {
+            const int c1 = tid + k * NT;
+            if (c1 >= 1 && c1 < T.W && (c1 - 1) / bsz < nfull) {
+                const double ur = new_entry(rv1[k], is_prow, coef_r, frow[c1], c1 == cstar, q);
+                const double uc = new_entry(cv1[k], false, coef0, frow[c1], c1 == cstar, q);
+                const double nc = priced_cost(uc, ur, coef0n, nzc, c1 == cn, qn);
+                int label = -1;
+                if (T.unres != nullptr && nc < 0) label = (c1 == cn) ? leaving : T.vcol[c1];
+                price_consider(T, acc, c1, nc, label, bsz);
+            }
         }
         price_finish(T, s, acc, &found, &neg);
     }
@@ -487,6 +513,16 @@ __device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const 
     int rnext, cnt;
     if (!cta_collect_partials(T, s, G, (unsigned int)(launch + 1), &rnext, &cnt)) return;  // S1 reports the error
     if (rnext < 0) return;
+    if (tid == 0) {  // the other selector must also be done reading the prow buffer (slot G is its message)
+        double dq;
+        int d1, d2, d3;
+        const long long tstart = clock64();
+        while (!part_try_read(T.part + G, (unsigned int)(launch + 1), &dq, &d1, &d2, &d3)) {
+            __nanosleep(20);
+            if (clock64() - tstart > 4000000000LL) break;
+        }
+    }
+    __syncthreads();
     const double *src = T.M;
     const double *rowp = src + (size_t)rnext * T.stride;
     const bool is_prow = rnext == rstar;
@@ -569,40 +605,31 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         const int lw = (NT >> 5) - 1;           // the warp that runs the look-ahead (last warp)
         const int lane = tid & 31;
         const bool la_warp = (tid >> 5) == lw && b < G;
-        double la_col = 0.0, la_rhs = 0.0, la_coef = 0.0;
-        if (la_warp && lane < nr) {  // this lane's row: pivot-column entry and the look-ahead operands
-            const size_t off = (size_t)(r0 + lane) * T.stride;
-            la_coef = ldg_cg(T.M + off + cstar);
-            if (want_partial) {
-                la_col = ldg_cg(T.M + off + next_c);
-                la_rhs = ldg_cg(T.M + off);
+        if (la_warp) {
+            // Look-ahead ratio test of the NEXT pivot on this CTA's rows as this pivot leaves them: one
+            // warp, shuffles only, published as one 16-byte message.  It needs just two entries of the
+            // normalised pivot row (computed here from the raw side buffer), so it neither waits for the
+            // whole-row normalisation nor delays the other warps.
+            double la_col = 0.0, la_rhs = 0.0, la_coef = 0.0, raw_n = 0.0, raw_0 = 0.0;
+            if (lane < nr) {  // this lane's row: pivot-column entry and the look-ahead operands
+                const size_t off = (size_t)(r0 + lane) * T.stride;
+                la_coef = ldg_cg(T.M + off + cstar);
+                if (want_partial) {
+                    la_col = ldg_cg(T.M + off + next_c);
+                    la_rhs = ldg_cg(T.M + off);
+                }
             }
-            s_coef[lane] = la_coef;
-        }
-        mbar_wait(&bar, 0);
-        for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
-            const double v = frow[c];
-            double f = nz16(v) ? v / q : 0.0;
-            if (c == cstar) f = 1.0 / q;
-            if (flush && !nz16(f) && f != 0.0) f = 0.0;
-            frow[c] = f;
-        }
-        __syncthreads();
-        if (dbg && tid == 0) t1 = clock64();
-        if (b == G) {
-            long long ts[3] = {0, 0, 0};
-            cta_selector_decide(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after, ts);
-            if (dbg && tid == 0) { t2 = ts[0]; t3 = ts[1]; g0 = ts[2] - t0; }  // partials in, reduced, first pricing pass
-        } else if (b == G + 1) {
-            cta_selector_stage(T, rec, sel, frow, G, rstar, cstar, q, next_c, launch, stop_after);
-            if (dbg && tid == 0) t2 = t3 = clock64();
-        } else {
-            if (la_warp && want_partial) {
-                // ratio test of the NEXT pivot on this CTA's rows as this pivot leaves them (one warp,
-                // shuffles only), published as one 16-byte message; the other warps are already streaming
+            if (want_partial) { raw_n = ldg_cg(prow_arg + next_c); raw_0 = ldg_cg(prow_arg); }
+            if (lane < nr) s_coef[lane] = la_coef;
+            if (want_partial) {
+                double f_n = nz16(raw_n) ? raw_n / q : 0.0;
+                if (next_c == cstar) f_n = 1.0 / q;
+                if (flush && !nz16(f_n) && f_n != 0.0) f_n = 0.0;
+                double f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
+                if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
                 const bool is_prow = (r0 + lane) == rstar;
-                const double col = new_entry(la_col, is_prow, la_coef, frow[next_c], next_c == cstar, q);
-                const double rhs = new_entry(la_rhs, is_prow, la_coef, frow[0], false, q);
+                const double col = new_entry(la_col, is_prow, la_coef, f_n, next_c == cstar, q);
+                const double rhs = new_entry(la_rhs, is_prow, la_coef, f_0, false, q);
                 const double prec = T.prec;
                 VI m = {INFINITY, INT_MAX};
                 int dmin = INT_MAX, cnt = 0;
@@ -626,12 +653,34 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                     dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
                     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
                 }
-                if (lane == 0)
+                if (lane == 0) {
+                    mbar_wait(&bar, 0);  // a published partial also promises: this CTA is done reading prow
                     part_publish(T.part + b, m.v, m.i == INT_MAX ? 255 : m.i, dmin == INT_MAX ? 255 : dmin, cnt,
                                  (unsigned int)(launch + 1));
+                    if (dbg) T.dbg[((size_t)launch * T.dbg_grid + b) * 8 + 2] = clock64() - s_t0;
+                }
             }
-            if (dbg && tid == NT - 32)  // publish time of the look-ahead warp
-                T.dbg[((size_t)launch * T.dbg_grid + b) * 8 + 2] = clock64() - s_t0;
+        }
+        mbar_wait(&bar, 0);
+        for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
+            const double v = frow[c];
+            double f = nz16(v) ? v / q : 0.0;
+            if (c == cstar) f = 1.0 / q;
+            if (flush && !nz16(f) && f != 0.0) f = 0.0;
+            frow[c] = f;
+        }
+        __syncthreads();
+        if (dbg && tid == 0) t1 = clock64();
+        if (b == G) {
+            long long ts[3] = {0, 0, 0};
+            // tell the staging selector that this CTA's TMA read of the prow buffer has landed
+            if (tid == 0) part_publish(T.part + G, 0.0, 255, 255, 0, (unsigned int)(launch + 1));
+            cta_selector_decide(Tp, T, rec, sel, frow, G, rstar, cstar, q, next_c, next_neg, launch, p2, log_n0, stop_after, ts);
+            if (dbg && tid == 0) { t2 = ts[0]; t3 = ts[1]; g0 = ts[2] - t0; }  // partials in, reduced, first pricing pass
+        } else if (b == G + 1) {
+            cta_selector_stage(T, rec, sel, frow, G, rstar, cstar, q, next_c, launch, stop_after);
+            if (dbg && tid == 0) t2 = t3 = clock64();
+        } else {
             update_rows_pp<RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
             if (dbg && tid == 0) t3 = clock64();
         }
