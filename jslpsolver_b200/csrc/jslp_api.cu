@@ -366,7 +366,7 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
             t->host_log.clear();
             return JSLP_OK;
         case JSLP_OPT_STEP_VARIANT:
-            if (value < 0 || value >= 7) return fail(JSLP_E_INVALID, "step variant out of range");
+            if (value < 0 || value >= 10) return fail(JSLP_E_INVALID, "step variant out of range");
             t->variant = (int)value;
             return JSLP_OK;
         case JSLP_OPT_GRID_PER_SM:
@@ -421,6 +421,9 @@ static const StepVariant STEP_VARIANTS[] = {
     {k_pivot_step<256, 3, 4, true>, 256, 3, "t256 occ3 rc4 prefetch"},
     {k_pivot_step<128, 8, 4, false>, 128, 8, "t128 occ8 rc4"},
     {k_pivot_step<256, 4, 2, true>, 256, 4, "t256 occ4 rc2 prefetch"},
+    {k_pivot_step<256, 2, 8, true>, 256, 2, "t256 occ2 rc8 prefetch"},
+    {k_pivot_step<384, 1, 8, true>, 384, 1, "t384 occ1 rc8 prefetch"},
+    {k_pivot_step<512, 1, 8, true>, 512, 1, "t512 occ1 rc8 prefetch"},
 };
 static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VARIANTS[0]));
 static const int SMALL_BATCH = 24;  // steps in the first graph of a solve

@@ -86,6 +86,9 @@ struct Rec {
     int next_c;      // entering column of the NEXT pivot, priced on the cost row as it will be after
                      // the staged pivot: -1 unknown (generic tail), 0 none (optimal), >0 column
     int next_neg;    // its isReducedCostNegative
+    int prow_norm;   // 1 = the prow side buffer already holds the NORMALISED pivot row (staged by the
+                     // ping-pong selector), 0 = the raw row (every CTA normalises it after the TMA copy)
+    int pad1;
     double q;        // raw pivot element
     double eval_raw; // matrix[0] at exit
 };
@@ -413,6 +416,7 @@ __device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar,
         rec->flush = (cnt - (nz16(q) ? 1 : 0)) > 0;
         rec->has_pivot = 1;
         rec->next_c = -1;  // the pivot after this one has not been priced
+        rec->prow_norm = 0;
     }
 }
 

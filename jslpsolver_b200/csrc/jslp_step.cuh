@@ -244,6 +244,7 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
         rec->flush = (cnt - (nz16(q) ? 1 : 0)) > 0;
         rec->has_pivot = 1;
         rec->next_c = found; rec->next_neg = neg;
+        rec->prow_norm = 0;
     }
 }
 
@@ -259,7 +260,7 @@ __device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G,
 //     all while the row CTAs are still streaming.  The launch ends when the streaming ends.
 
 // dst rows [r0, r0+nr) = pivot applied to src rows (simplex.ts:352-391); every pair is written.
-template <int RC>
+template <int RC, bool PF>
 __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, int stride_i, const double *frow,
                                                const double *s_coef, int r0, int nr, int rstar, int cstar, double q) {
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -280,14 +281,9 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
         }
         const double *sb = src + (size_t)rb * stride;
         double *db = dst + (size_t)rb * stride;
-        for (int c2 = tid; c2 < npair; c2 += NT) {
-            const double2 f = frow2[c2];
+        auto emit = [&](int c2, const double2 f, const double2 *old) {
             const bool z0 = nz16(f.x), z1 = nz16(f.y);
             const bool pc = (c2 == cpair);
-            double2 old[RC];
-#pragma unroll
-            for (int j = 0; j < RC; j++)
-                if (valid[j] && !isp[j]) old[j] = ld_v2(sb + j * stride + 2 * c2);
 #pragma unroll
             for (int j = 0; j < RC; j++) {
                 if (!valid[j]) continue;
@@ -299,6 +295,36 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
                     if (pc && coef[j] != 0.0) { if (codd) nv.y = 0.0; else nv.x = 0.0; }  // simplex.ts:386-388
                 }
                 st_v2(db + j * stride + 2 * c2, nv);
+            }
+        };
+        if (!PF) {
+            for (int c2 = tid; c2 < npair; c2 += NT) {
+                double2 old[RC];
+#pragma unroll
+                for (int j = 0; j < RC; j++)
+                    if (valid[j] && !isp[j]) old[j] = ld_v2(sb + j * stride + 2 * c2);
+                emit(c2, frow2[c2], old);
+            }
+        } else {  // software prefetch: the next pair's RC loads are in flight while this pair is stored
+            int c2 = tid;
+            double2 old[RC];
+            if (c2 < npair) {
+#pragma unroll
+                for (int j = 0; j < RC; j++)
+                    if (valid[j] && !isp[j]) old[j] = ld_v2(sb + j * stride + 2 * c2);
+            }
+            while (c2 < npair) {
+                const int n2 = c2 + NT;
+                double2 oldn[RC];
+                if (n2 < npair) {
+#pragma unroll
+                    for (int j = 0; j < RC; j++)
+                        if (valid[j] && !isp[j]) oldn[j] = ld_v2(sb + j * stride + 2 * n2);
+                }
+                emit(c2, frow2[c2], old);
+                c2 = n2;
+#pragma unroll
+                for (int j = 0; j < RC; j++) old[j] = oldn[j];
             }
         }
     }
@@ -500,6 +526,7 @@ __device__ void cta_selector_decide(TabDev *Tp, const TabDev &T, Rec *rec, SelSm
         rec->flush = (cnt - (nz16(qn) ? 1 : 0)) > 0;
         rec->has_pivot = 1;
         rec->next_c = found; rec->next_neg = neg;
+        rec->prow_norm = 1;  // the staging selector writes the normalised row
         flip();
     }
 }
@@ -527,6 +554,10 @@ __device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const 
     const double *rowp = src + (size_t)rnext * T.stride;
     const bool is_prow = rnext == rstar;
     const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
+    // pivot element and lazy-flush flag of the next pivot: the row is staged already NORMALISED
+    // (simplex.ts:352-364, 380-382), so no CTA of the next launch has to divide it again
+    const double qn = new_entry(ldg_cg(rowp + cn), is_prow, coef_r, frow[cn], cn == cstar, q);
+    const bool flushn = (cnt - (nz16(qn) ? 1 : 0)) > 0;
     for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
         double rv[8];
 #pragma unroll
@@ -538,7 +569,14 @@ __device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const 
         for (int k = 0; k < 8; k++) {
             const int c = c0 + tid + k * NT;
             if (c >= T.stride) continue;
-            T.prow[c] = c < T.W ? new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q) : 0.0;
+            double f = 0.0;
+            if (c < T.W) {
+                const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
+                f = nz16(ur) ? ur / qn : 0.0;
+                if (c == cn) f = 1.0 / qn;
+                if (flushn && !nz16(f) && f != 0.0) f = 0.0;
+            }
+            T.prow[c] = f;
         }
     }
     (void)rec;
@@ -583,6 +621,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     const int p1 = rec->p1, p2 = rec->p2, log_n0 = rec->log_n;
     const double q = rec->q;
     const int next_c = rec->next_c, next_neg = rec->next_neg, lookahead = rec->lookahead;
+    const int prow_norm = rec->prow_norm;
     const bool stop_after = stop_at >= 0 && launch + 1 >= stop_at;
     __syncthreads();
     const bool dbg = T.dbg != nullptr && launch < T.dbg_cap;
@@ -622,11 +661,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             if (want_partial) { raw_n = ldg_cg(prow_arg + next_c); raw_0 = ldg_cg(prow_arg); }
             if (lane < nr) s_coef[lane] = la_coef;
             if (want_partial) {
-                double f_n = nz16(raw_n) ? raw_n / q : 0.0;
-                if (next_c == cstar) f_n = 1.0 / q;
-                if (flush && !nz16(f_n) && f_n != 0.0) f_n = 0.0;
-                double f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
-                if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
+                double f_n = raw_n, f_0 = raw_0;
+                if (!prow_norm) {
+                    f_n = nz16(raw_n) ? raw_n / q : 0.0;
+                    if (next_c == cstar) f_n = 1.0 / q;
+                    if (flush && !nz16(f_n) && f_n != 0.0) f_n = 0.0;
+                    f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
+                    if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
+                }
                 const bool is_prow = (r0 + lane) == rstar;
                 const double col = new_entry(la_col, is_prow, la_coef, f_n, next_c == cstar, q);
                 const double rhs = new_entry(la_rhs, is_prow, la_coef, f_0, false, q);
@@ -662,12 +704,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             }
         }
         mbar_wait(&bar, 0);
-        for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
-            const double v = frow[c];
-            double f = nz16(v) ? v / q : 0.0;
-            if (c == cstar) f = 1.0 / q;
-            if (flush && !nz16(f) && f != 0.0) f = 0.0;
-            frow[c] = f;
+        if (!prow_norm) {
+            for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
+                const double v = frow[c];
+                double f = nz16(v) ? v / q : 0.0;
+                if (c == cstar) f = 1.0 / q;
+                if (flush && !nz16(f) && f != 0.0) f = 0.0;
+                frow[c] = f;
+            }
         }
         __syncthreads();
         if (dbg && tid == 0) t1 = clock64();
@@ -681,7 +725,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             cta_selector_stage(T, rec, sel, frow, G, rstar, cstar, q, next_c, launch, stop_after);
             if (dbg && tid == 0) t2 = t3 = clock64();
         } else {
-            update_rows_pp<RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
+            update_rows_pp<RC, PF>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
             if (dbg && tid == 0) t3 = clock64();
         }
         if (dbg && tid == 0) {
@@ -712,12 +756,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     }
 
     mbar_wait(&bar, 0);
-    for (int c = tid; c < T.stride; c += NT) {  // normalise in place (simplex.ts:352-364, 380-382)
-        const double v = frow[c];
-        double f = nz16(v) ? v / q : 0.0;
-        if (c == cstar) f = 1.0 / q;
-        if (flush && !nz16(f) && f != 0.0) f = 0.0;
-        frow[c] = f;
+    if (!prow_norm) {
+        for (int c = tid; c < T.stride; c += NT) {  // normalise in place (simplex.ts:352-364, 380-382)
+            const double v = frow[c];
+            double f = nz16(v) ? v / q : 0.0;
+            if (c == cstar) f = 1.0 / q;
+            if (flush && !nz16(f) && f != 0.0) f = 0.0;
+            frow[c] = f;
+        }
     }
     __syncthreads();
     if (dbg && tid == 0) t1 = clock64();
