@@ -120,7 +120,7 @@ struct jslp_tab {
     int isIntegralFlag = 0, bncIterations = 0;
     // options
     int engine = 0, batch = 256;
-    int variant = 0, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0, pingpong = 1;
+    int variant = 1, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0, pingpong = 1;
     int64_t host_log_cap = 0;
     std::vector<int4> host_log;
     // graphs
