@@ -174,6 +174,8 @@ typedef struct {
     double best_possible_eval;
     double gpu_ms;
     int64_t kernel_launches;
+    double host_eval_ms;   /* wall time spent evaluating node batches (launch + read-back + sync) */
+    double host_commit_ms; /* wall time spent in the sequential commit loop                     */
 } jslp_bnb_status;
 
 int jslp_branch_and_cut(jslp_tab *root, const jslp_bnb_opts *opts, jslp_bnb_status *out,

@@ -43,7 +43,8 @@ class BnbStatus(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("feasible", "bounded", "is_integral", "iterations", "n_best_cuts",
                                          "rounds")] + [
         ("nodes_evaluated", C.c_int64), ("pivots", C.c_int64), ("evaluation", C.c_double),
-        ("best_possible_eval", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int64)]
+        ("best_possible_eval", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int64),
+        ("host_eval_ms", C.c_double), ("host_commit_ms", C.c_double)]
 
 
 # every symbol include/jslp_b200.h declares: (name, restype, argtypes)

@@ -380,7 +380,7 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
             t->pingpong = value != 0;
             return JSLP_OK;
         case JSLP_OPT_PDL:
-            t->pdl = value != 0;
+            t->pdl = (int)value;  // 1 = PDL edges inside the graph, 2 = PDL-chained plain launches
             return JSLP_OK;
         case JSLP_OPT_TIMELINE:
             if (value < 0 || value > 4096) return fail(JSLP_E_INVALID, "timeline launches must be 0..4096");
@@ -465,7 +465,7 @@ static int build_graphs(jslp_tab *t) {
     int rc = ensure_step_bufs(t, grid);
     if (rc) return rc;
     if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem &&
-        t->g_variant == t->variant + 100 * t->pdl + 1000 * t->pingpong)
+        t->g_variant == t->variant + 100 * (t->pdl == 1) + 1000 * t->pingpong)
         return JSLP_OK;
     drop_graphs(t);
     cudaStream_t s = t->ctx->stream;
@@ -481,7 +481,7 @@ static int build_graphs(jslp_tab *t) {
         if ((mode & 1) == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
             k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
             for (int i = 0; i < nsteps; i++) {
-                if (t->pdl && i > 0) {
+                if (t->pdl == 1 && i > 0) {
                     // programmatic dependent launch: step i's CTAs are scheduled while step i-1
                     // drains and block in griddepcontrol.wait until it has completed
                     cudaLaunchConfig_t cfg;
@@ -519,7 +519,7 @@ static int build_graphs(jslp_tab *t) {
         if (mode == 0) t->g_fused = ge; else if (mode == 1) t->g_simple = ge;
         else if (mode == 2) t->g_fused_small = ge; else t->g_simple_small = ge;
     }
-    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * t->pdl + 1000 * t->pingpong;
+    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * (t->pdl == 1) + 1000 * t->pingpong;
     return JSLP_OK;
 }
 
@@ -769,7 +769,29 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             int e = snapshot_copy(t, slot, true);
             if (e) return e;
         }
-        CK(cudaGraphLaunch(graphs[kind], s));
+        if (t->pdl == 2 && engine == 2) {
+            // experiment: plain stream launches chained by programmatic dependent launch (no graph)
+            const StepVariant &sv = step_variant(t);
+            const int grid = step_grid(t), smem = t->stride * 8;
+            const int fused_mode = (t->pingpong && t->lookahead && grid >= 3) ? 2 : 1;
+            k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
+            k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
+            for (int i = 0; i < sizes[kind]; i++) {
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sv.threads);
+                cfg.dynamicSmemBytes = smem; cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = i > 0 ? 1 : 0;
+                TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = fused_mode; const double *a3 = t->hd.prow; int a4 = t->stride;
+                void *args[] = {&a0, &a1, &a2, &a3, &a4};
+                CK(cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args));
+            }
+        } else {
+            CK(cudaGraphLaunch(graphs[kind], s));
+        }
         ctx->launches += launches_of(kind);
         CK(cudaMemcpyAsync(t->h_rec + slot, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(t->h_log + (size_t)slot * cap, t->hd.plog, sizeof(int4) * (size_t)cap, cudaMemcpyDeviceToHost, s));

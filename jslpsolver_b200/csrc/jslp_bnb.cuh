@@ -11,6 +11,7 @@
 // result ends the round.  Speculation that is never popped is wasted work, never wrong work.
 #pragma once
 
+#include <chrono>
 #include <map>
 #include <memory>
 
@@ -308,6 +309,11 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         return 0;
     };
 
+    double eval_ms = 0, commit_ms = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     branches.push(std::unique_ptr<Branch>(new Branch{-INFINITY, {}, NodeEval()}));
     bool stop = false;
     while (!stop && !branches.empty() && toleranceFlag) {
@@ -322,12 +328,16 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             if (!(e.b->relaxedEvaluation > bestEvaluation) && !e.b->ev.valid) todo.push_back(e.b.get());
             taken.push_back(std::move(e));
         }
+        const auto t_eval = now();
         if (!todo.empty()) {
             rounds++;
             std::vector<Branch *> mine;
             int maxc = 0;
+            // the root round is NOT sharded: every rank needs the solved root in its own tableau, it is
+            // what jslp_save snapshots and what every later node is derived from
+            const bool sharded = n_ranks > 1 && iterations > 0;
             for (size_t i = 0; i < todo.size(); i++)
-                if ((int)(i % n_ranks) == rank) {
+                if (!sharded || (int)(i % n_ranks) == rank) {
                     mine.push_back(todo[i]);
                     maxc = std::max(maxc, (int)todo[i]->cuts.size());
                 }
@@ -344,7 +354,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             }
             nodes += (int64_t)mine.size();
             if (todo.size() > 1) speculated = true;
-            if (n_ranks > 1) {  // all-gather the summaries: rank-major blocks of `per` records
+            if (sharded) {  // all-gather the summaries: rank-major blocks of `per` records
                 const int per = (int)((todo.size() + n_ranks - 1) / n_ranks);
                 wire.assign((size_t)per * n_ranks * WIRE_DOUBLES, 0.0);
                 for (size_t j = 0; j < mine.size(); j++)
@@ -356,6 +366,8 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             }
         }
         for (auto &e : taken) branches.push_entry(std::move(e));  // original seq: order unchanged
+        eval_ms += ms_since(t_eval);
+        const auto t_commit = now();
 
         // ---- commit sequentially in the reference's exact order ---------------------------------
         while (!branches.empty() && toleranceFlag) {
@@ -373,6 +385,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             if (rc < 0) return rc;
             if (rc == 1) { stop = true; break; }
         }
+        commit_ms += ms_since(t_commit);
     }
 
     // Final tableau: the reference re-solves the winner (branch-and-cut.ts:195-197); without a
@@ -410,6 +423,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         out->nodes_evaluated = nodes; out->pivots = pivots; out->evaluation = t->evaluation;
         out->best_possible_eval = t->bestPossibleEval; out->gpu_ms = ms;
         out->kernel_launches = ctx->launches - launches0;
+        out->host_eval_ms = eval_ms; out->host_commit_ms = commit_ms;
     }
     return JSLP_OK;
 }

@@ -346,11 +346,12 @@ __device__ __forceinline__ void part_publish(Part *slot, double minq, int minr_r
                                  ((unsigned long long)part_chk(a, seq & 0xffffffu) << 48);
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(a), "l"(b) : "memory");
 }
-// returns true when the slot holds the publication tagged `seq`
-__device__ __forceinline__ bool part_try_read(const Part *slot, unsigned int seq, double *minq, int *minr_rel,
-                                              int *dmin_rel, int *cnt) {
-    unsigned long long a, b;
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(slot) : "memory");
+// raw 16-byte probe of a slot / validation of a probe against the publication tagged `seq`
+__device__ __forceinline__ void part_probe(const Part *slot, unsigned long long *a, unsigned long long *b) {
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(slot) : "memory");
+}
+__device__ __forceinline__ bool part_decode(unsigned long long a, unsigned long long b, unsigned int seq, double *minq,
+                                            int *minr_rel, int *dmin_rel, int *cnt) {
     if ((unsigned int)(b & 0xffffffull) != (seq & 0xffffffu)) return false;
     if ((unsigned int)(b >> 48) != part_chk(a, seq & 0xffffffu)) return false;
     *minq = __longlong_as_double((long long)a);
@@ -358,6 +359,12 @@ __device__ __forceinline__ bool part_try_read(const Part *slot, unsigned int seq
     *minr_rel = (int)((b >> 32) & 0xff);
     *dmin_rel = (int)((b >> 40) & 0xff);
     return true;
+}
+__device__ __forceinline__ bool part_try_read(const Part *slot, unsigned int seq, double *minq, int *minr_rel,
+                                              int *dmin_rel, int *cnt) {
+    unsigned long long a, b;
+    part_probe(slot, &a, &b);
+    return part_decode(a, b, seq, minq, minr_rel, dmin_rel, cnt);
 }
 
 // Selector side: wait for all G partials of this launch and reduce them (simplex.ts:271-296 over the
@@ -374,31 +381,37 @@ __device__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigne
         for (int k = 0; k < 4; k++)
             if (b0 + tid + k * NT < G) pending |= 1u << k;
         while (pending) {
-            double pq[4];
-            int mr[4], dr[4], pc[4];
-            bool got[4];
+            // Pipelined polling: a probe takes 1.5-2.5 us to come back while the row CTAs stream, so three
+            // probes per slot are issued 250 ns apart BEFORE the first answer is consumed; a publication
+            // is then seen within one probe latency + 250 ns instead of up to two latencies.
+            unsigned long long pa[3][4], pb[3][4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                got[k] = false;
-                if (pending & (1u << k)) got[k] = part_try_read(T.part + b0 + tid + k * NT, seq, &pq[k], &mr[k], &dr[k], &pc[k]);
+            for (int p = 0; p < 3; p++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (pending & (1u << k)) part_probe(T.part + b0 + tid + k * NT, &pa[p][k], &pb[p][k]);
+                if (p < 2) __nanosleep(250);
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (!got[k]) continue;
-                pending &= ~(1u << k);
-                const int b = b0 + tid + k * NT;
-                const int r0 = b * base + min(b, rem);
-                cnt += pc[k];
-                if (dr[k] != 255 && r0 + dr[k] < dmin) dmin = r0 + dr[k];
-                if (mr[k] != 255) {
-                    const int pr = r0 + mr[k];
-                    if (pq[k] < m.v || (pq[k] == m.v && pr < m.i)) { m.v = pq[k]; m.i = pr; }
+            for (int p = 0; p < 3; p++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (!(pending & (1u << k))) continue;
+                    double pq;
+                    int mr, dr, pc;
+                    if (!part_decode(pa[p][k], pb[p][k], seq, &pq, &mr, &dr, &pc)) continue;
+                    pending &= ~(1u << k);
+                    const int b = b0 + tid + k * NT;
+                    const int r0 = b * base + min(b, rem);
+                    cnt += pc;
+                    if (dr != 255 && r0 + dr < dmin) dmin = r0 + dr;
+                    if (mr != 255) {
+                        const int pr = r0 + mr;
+                        if (pq < m.v || (pq == m.v && pr < m.i)) { m.v = pq; m.i = pr; }
+                    }
                 }
             }
-            if (pending) {
-                __nanosleep(20);
-                if (clock64() - tstart > 4000000000LL) { ok = 0; break; }
-            }
+            if (pending && clock64() - tstart > 4000000000LL) { ok = 0; break; }
         }
     }
     ok = block_reduce_int<0>(ok, s.red);

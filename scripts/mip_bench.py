@@ -77,7 +77,8 @@ def main():
                        "gpu_ms": b.gpu_ms, "iterations": b.iterations, "rounds": b.rounds,
                        "node_lps": b.nodes_evaluated, "pivots": b.pivots, "launches": b.kernel_launches,
                        "node_lps_per_s": b.nodes_evaluated * world / (b.gpu_ms * 1e-3) if world == 1 else None,
-                       "committed_nodes_per_s": b.iterations / (b.gpu_ms * 1e-3), "result": sol.evaluation}
+                       "committed_nodes_per_s": b.iterations / (b.gpu_ms * 1e-3), "result": sol.evaluation,
+                       "host_eval_ms": b.host_eval_ms, "host_commit_ms": b.host_commit_ms}
                 if best is None or rec["gpu_ms"] < best["gpu_ms"]:
                     best = rec
             if rank == 0:
