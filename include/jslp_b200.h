@@ -176,6 +176,9 @@ typedef struct {
     int64_t kernel_launches;
     double host_eval_ms;   /* wall time spent evaluating node batches (launch + read-back + sync) */
     double host_commit_ms; /* wall time spent in the sequential commit loop                     */
+    double host_root_ms;   /* part of host_eval_ms spent on the root relaxation                 */
+    double host_final_ms;  /* wall time of the final re-solve of the winning branch             */
+    double node_kernel_ms; /* sum over rounds of the slowest node CTA's lifetime (%globaltimer) */
 } jslp_bnb_status;
 
 int jslp_branch_and_cut(jslp_tab *root, const jslp_bnb_opts *opts, jslp_bnb_status *out,

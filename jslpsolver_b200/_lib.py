@@ -44,7 +44,8 @@ class BnbStatus(C.Structure):
                                          "rounds")] + [
         ("nodes_evaluated", C.c_int64), ("pivots", C.c_int64), ("evaluation", C.c_double),
         ("best_possible_eval", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int64),
-        ("host_eval_ms", C.c_double), ("host_commit_ms", C.c_double)]
+        ("host_eval_ms", C.c_double), ("host_commit_ms", C.c_double),
+        ("host_root_ms", C.c_double), ("host_final_ms", C.c_double), ("node_kernel_ms", C.c_double)]
 
 
 # every symbol include/jslp_b200.h declares: (name, restype, argtypes)

@@ -64,36 +64,52 @@ struct NodeLogEntry {
 };
 
 // Host/device staging for batches of shared-memory-resident node LPs (k_node_batch).
+// Buffers of the shared-memory-resident node path.  Inputs (cut lists) and outputs (NodeOut records)
+// live in MAPPED pinned host memory: the kernel reads/writes them across PCIe itself, so a round is
+// one launch + one stream sync with no copy operations on the stream.
 struct ResidentBufs {
-    CutDev *d_cuts = nullptr, *h_cuts = nullptr;
-    int *d_off = nullptr, *h_off = nullptr;
-    NodeResult *d_res = nullptr, *h_res = nullptr;
-    int4 *d_logs = nullptr, *h_logs = nullptr;
-    int cap_nodes = 0, cap_cuts = 0, log_cap = 0, smem_set = 0;
+    CutDev *h_cuts = nullptr, *dv_cuts = nullptr;   // host pointer / device alias
+    int *h_off = nullptr, *dv_off = nullptr;
+    NodeOut *h_out = nullptr, *dv_out = nullptr;
+    int4 *d_logs = nullptr, *h_logs = nullptr;      // full logs: device memory, fetched only when needed
+    int cap_nodes = 0, cap_cuts = 0;
+    size_t cap_log_entries = 0;
+    int smem_set = 0;
     void release() {
-        cudaFree(d_cuts); cudaFree(d_off); cudaFree(d_res); cudaFree(d_logs);
-        cudaFreeHost(h_cuts); cudaFreeHost(h_off); cudaFreeHost(h_res); cudaFreeHost(h_logs);
-        d_cuts = h_cuts = nullptr; d_off = h_off = nullptr; d_res = h_res = nullptr; d_logs = h_logs = nullptr;
-        cap_nodes = cap_cuts = log_cap = 0;
+        cudaFree(d_logs);
+        cudaFreeHost(h_cuts); cudaFreeHost(h_off); cudaFreeHost(h_out); cudaFreeHost(h_logs);
+        h_cuts = dv_cuts = nullptr; h_off = dv_off = nullptr; h_out = dv_out = nullptr; d_logs = h_logs = nullptr;
+        cap_nodes = cap_cuts = 0; cap_log_entries = 0;
+    }
+    template <typename T>
+    static int mapped(T **h, T **d, size_t bytes) {
+        CK(cudaHostAlloc((void **)h, bytes, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void **)d, (void *)*h, 0));
+        return JSLP_OK;
     }
     int ensure(int n, int totc, int lc) {
-        if (n > cap_nodes || lc != log_cap) {
-            const int cn = std::max(64, std::max(n, cap_nodes) * 2);
-            cudaFree(d_off); cudaFree(d_res); cudaFree(d_logs);
-            cudaFreeHost(h_off); cudaFreeHost(h_res); cudaFreeHost(h_logs);
-            CK(cudaMalloc(&d_off, sizeof(int) * (size_t)(cn + 1)));
-            CK(cudaMallocHost(&h_off, sizeof(int) * (size_t)(cn + 1)));
-            CK(cudaMalloc(&d_res, sizeof(NodeResult) * (size_t)cn));
-            CK(cudaMallocHost(&h_res, sizeof(NodeResult) * (size_t)cn));
-            CK(cudaMalloc(&d_logs, sizeof(int4) * (size_t)cn * lc));
-            CK(cudaMallocHost(&h_logs, sizeof(int4) * (size_t)cn * lc));
-            cap_nodes = cn; log_cap = lc;
+        int rc;
+        if (n > cap_nodes) {
+            const int cn = std::max(64, n * 2);
+            cudaFreeHost(h_off); cudaFreeHost(h_out);
+            h_off = nullptr; h_out = nullptr;
+            if ((rc = mapped(&h_off, &dv_off, sizeof(int) * (size_t)(cn + 1)))) return rc;
+            if ((rc = mapped(&h_out, &dv_out, sizeof(NodeOut) * (size_t)cn))) return rc;
+            cap_nodes = cn;
         }
-        if (totc > cap_cuts) {
+        if ((size_t)n * lc > cap_log_entries) {
+            const size_t ce = std::max((size_t)64 * 512, (size_t)n * lc * 2);
+            cudaFree(d_logs); cudaFreeHost(h_logs);
+            d_logs = nullptr; h_logs = nullptr;
+            CK(cudaMalloc(&d_logs, sizeof(int4) * ce));
+            CK(cudaMallocHost(&h_logs, sizeof(int4) * ce));
+            cap_log_entries = ce;
+        }
+        if (totc > cap_cuts || !h_cuts) {
             const int cc = std::max(1024, totc * 2);
-            cudaFree(d_cuts); cudaFreeHost(h_cuts);
-            CK(cudaMalloc(&d_cuts, sizeof(CutDev) * (size_t)cc));
-            CK(cudaMallocHost(&h_cuts, sizeof(CutDev) * (size_t)cc));
+            cudaFreeHost(h_cuts);
+            h_cuts = nullptr;
+            if ((rc = mapped(&h_cuts, &dv_cuts, sizeof(CutDev) * (size_t)cc))) return rc;
             cap_cuts = cc;
         }
         return JSLP_OK;
@@ -132,6 +148,7 @@ struct jslp_tab {
     Snapshot snaps[2];  // one restart point per in-flight batch
     std::vector<NodeLogEntry> node_log;
     ResidentBufs rbufs;
+    long long node_kernel_ns = 0;  // sum over rounds of the slowest node CTA (reporting)
 };
 
 extern "C" const char *jslp_last_error(void) { return g_err.c_str(); }
@@ -657,11 +674,10 @@ static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, b
     const int64_t launches0 = ctx->launches;
     if (timed) CK(cudaEventRecord(ctx->ev0, s));
     rb.h_off[0] = 0; rb.h_off[1] = 0;
-    CK(cudaMemcpyAsync(rb.d_off, rb.h_off, sizeof(int) * 2, cudaMemcpyHostToDevice, s));
     NodeBatchDev nb;
     memset(&nb, 0, sizeof(nb));
     nb.rootM = t->hd.M; nb.root_vrow = t->hd.vrow; nb.root_vcol = t->hd.vcol;
-    nb.cuts = rb.d_cuts; nb.cut_off = rb.d_off; nb.results = rb.d_res; nb.logs = rb.d_logs;
+    nb.cuts = rb.dv_cuts; nb.cut_off = rb.dv_off; nb.out = rb.dv_out; nb.logs = rb.d_logs;
     nb.wb_M = snap.M; nb.wb_vrow = snap.vrow; nb.wb_vcol = snap.vcol;
     nb.H0 = t->H; nb.root_stride = t->stride; nb.first_index = t->lastElementIndex;
     nb.Hcap = t->H; nb.Ws = Ws; nb.log_cap = log_cap; nb.max_pivots = log_cap - 2;
@@ -672,11 +688,15 @@ static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, b
     k_node_batch<<<1, NODE_THREADS, smem, s>>>(t->d_T, nb);
     ctx->launches += 1;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(rb.h_res, rb.d_res, sizeof(NodeResult), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)log_cap, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const NodeResult r = rb.h_res[0];
+    const NodeResult r = rb.h_out[0].r;
     if (r.overflow || r.log_n > log_cap) return JSLP_OK;
+    if (r.log_n <= NODE_LOG_HEAD) {
+        memcpy(rb.h_logs, rb.h_out[0].log_head, sizeof(int4) * (size_t)r.log_n);
+    } else {
+        CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)r.log_n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     if (check_cycles) {
         std::vector<long long> h1, h2;
         int cs, cl;

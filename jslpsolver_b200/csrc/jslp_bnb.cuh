@@ -128,7 +128,8 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
 static size_t node_smem_bytes(int Hcap, int W, int *Ws_out) {
     const int Ws = (W & 1) ? W : W + 1;  // odd row stride: conflict-free column walks
     if (Ws_out) *Ws_out = Ws;
-    return sizeof(double) * ((size_t)Hcap * Ws + 2 * (size_t)Ws + Hcap) + sizeof(int) * ((size_t)Hcap + W) + 16;
+    return sizeof(double) * ((size_t)Hcap * Ws + 2 * (size_t)Ws + Hcap) + sizeof(CutDev) * (size_t)Hcap +
+           sizeof(int) * ((size_t)Hcap + W) + 16;
 }
 
 static bool resident_fits(const jslp_tab *t, int Hcap) {
@@ -161,12 +162,10 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
         }
     }
     rb.h_off[n] = off;
-    if (totc > 0) CK(cudaMemcpyAsync(rb.d_cuts, rb.h_cuts, sizeof(CutDev) * (size_t)totc, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(rb.d_off, rb.h_off, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
     NodeBatchDev nb;
     memset(&nb, 0, sizeof(nb));
     nb.rootM = t->saved.M; nb.root_vrow = t->saved.vrow; nb.root_vcol = t->saved.vcol;
-    nb.cuts = rb.d_cuts; nb.cut_off = rb.d_off; nb.results = rb.d_res; nb.logs = rb.d_logs;
+    nb.cuts = rb.dv_cuts; nb.cut_off = rb.dv_off; nb.out = rb.dv_out; nb.logs = rb.d_logs;
     nb.H0 = t->saved.H; nb.root_stride = t->stride; nb.first_index = t->saved.lastElementIndex;
     nb.Hcap = Hcap; nb.Ws = Ws; nb.log_cap = log_cap; nb.max_pivots = 100000;
     if ((int)smem > rb.smem_set) {
@@ -176,18 +175,26 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
     k_node_batch<<<n, NODE_THREADS, smem, s>>>(t->d_T, nb);
     ctx->launches += 1;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(rb.h_res, rb.d_res, sizeof(NodeResult) * (size_t)n, cudaMemcpyDeviceToHost, s));
-    if (check_cycles)
-        CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)n * log_cap, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(s));  // inputs and outputs are mapped host memory: nothing to copy
+    long long slowest = 0;
+    bool need_full = false;
     for (int i = 0; i < n; i++) {
-        const NodeResult &r = rb.h_res[i];
+        slowest = std::max(slowest, rb.h_out[i].r.t_ns);
+        if (check_cycles && !rb.h_out[i].r.overflow && rb.h_out[i].r.log_n > NODE_LOG_HEAD) need_full = true;
+    }
+    t->node_kernel_ns += slowest;
+    if (need_full) {  // rare: a node with a long pivot sequence, fetch the complete logs
+        CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)n * log_cap, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    for (int i = 0; i < n; i++) {
+        const NodeResult &r = rb.h_out[i].r;
         jslp_bnb::NodeEval &ev = nodes[i]->ev;
         bool redo = r.overflow != 0;
         if (!redo && check_cycles) {
             std::vector<long long> h1, h2;
             int cs, cl;
-            const int4 *lg = rb.h_logs + (size_t)i * log_cap;
+            const int4 *lg = r.log_n > NODE_LOG_HEAD ? rb.h_logs + (size_t)i * log_cap : rb.h_out[i].log_head;
             for (int k = 0; k < r.log_n && k < log_cap && !redo; k++) {
                 std::vector<long long> &h = ((lg[k].x >> 30) & 1) ? h2 : h1;
                 h.push_back(((long long)lg[k].z << 32) | (unsigned int)lg[k].w);
@@ -309,7 +316,8 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         return 0;
     };
 
-    double eval_ms = 0, commit_ms = 0;
+    double eval_ms = 0, commit_ms = 0, root_ms = 0, final_ms = 0;
+    t->node_kernel_ns = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -366,6 +374,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             }
         }
         for (auto &e : taken) branches.push_entry(std::move(e));  // original seq: order unchanged
+        if (iterations == 0) root_ms += ms_since(t_eval);
         eval_ms += ms_since(t_eval);
         const auto t_commit = now();
 
@@ -394,6 +403,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
     if (!early_return) {
         const Branch *fin = bestBranch ? bestBranch.get() : lastCommitted.get();
         if (fin && (bestBranch || iterations > 1)) {
+            const auto t_fin = now();
             NodeEval ev;
             int rc = eval_node_streaming(t, *fin, check_cycles, ev);
             if (rc) return rc;
@@ -402,6 +412,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
                 pivots += ev.pivots;
                 if (ev.optimal) t->simplexIters += 1;
             }
+            final_ms = ms_since(t_fin);
         }
         (void)speculated;
         if (bestBranch) {
@@ -424,6 +435,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         out->best_possible_eval = t->bestPossibleEval; out->gpu_ms = ms;
         out->kernel_launches = ctx->launches - launches0;
         out->host_eval_ms = eval_ms; out->host_commit_ms = commit_ms;
+        out->host_root_ms = root_ms; out->host_final_ms = final_ms; out->node_kernel_ms = 1e-6 * (double)t->node_kernel_ns;
     }
     return JSLP_OK;
 }

@@ -381,37 +381,31 @@ __device__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigne
         for (int k = 0; k < 4; k++)
             if (b0 + tid + k * NT < G) pending |= 1u << k;
         while (pending) {
-            // Pipelined polling: a probe takes 1.5-2.5 us to come back while the row CTAs stream, so three
-            // probes per slot are issued 250 ns apart BEFORE the first answer is consumed; a publication
-            // is then seen within one probe latency + 250 ns instead of up to two latencies.
-            unsigned long long pa[3][4], pb[3][4];
+            double pq[4];
+            int mr[4], dr[4], pc[4];
+            bool got[4];
 #pragma unroll
-            for (int p = 0; p < 3; p++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (pending & (1u << k)) part_probe(T.part + b0 + tid + k * NT, &pa[p][k], &pb[p][k]);
-                if (p < 2) __nanosleep(250);
+            for (int k = 0; k < 4; k++) {
+                got[k] = false;
+                if (pending & (1u << k)) got[k] = part_try_read(T.part + b0 + tid + k * NT, seq, &pq[k], &mr[k], &dr[k], &pc[k]);
             }
 #pragma unroll
-            for (int p = 0; p < 3; p++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (!(pending & (1u << k))) continue;
-                    double pq;
-                    int mr, dr, pc;
-                    if (!part_decode(pa[p][k], pb[p][k], seq, &pq, &mr, &dr, &pc)) continue;
-                    pending &= ~(1u << k);
-                    const int b = b0 + tid + k * NT;
-                    const int r0 = b * base + min(b, rem);
-                    cnt += pc;
-                    if (dr != 255 && r0 + dr < dmin) dmin = r0 + dr;
-                    if (mr != 255) {
-                        const int pr = r0 + mr;
-                        if (pq < m.v || (pq == m.v && pr < m.i)) { m.v = pq; m.i = pr; }
-                    }
+            for (int k = 0; k < 4; k++) {
+                if (!got[k]) continue;
+                pending &= ~(1u << k);
+                const int b = b0 + tid + k * NT;
+                const int r0 = b * base + min(b, rem);
+                cnt += pc[k];
+                if (dr[k] != 255 && r0 + dr[k] < dmin) dmin = r0 + dr[k];
+                if (mr[k] != 255) {
+                    const int pr = r0 + mr[k];
+                    if (pq[k] < m.v || (pq[k] == m.v && pr < m.i)) { m.v = pq[k]; m.i = pr; }
                 }
             }
-            if (pending && clock64() - tstart > 4000000000LL) { ok = 0; break; }
+            if (pending) {
+                __nanosleep(20);
+                if (clock64() - tstart > 4000000000LL) { ok = 0; break; }
+            }
         }
     }
     ok = block_reduce_int<0>(ok, s.red);

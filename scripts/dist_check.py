@@ -24,9 +24,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # DIST_ONE_GPU=1: every rank on cuda:0 with the gloo backend -- exercises the sharded frontier
+    # logic on a single-GPU box (NCCL needs one device per rank)
+    one_gpu = os.environ.get("DIST_ONE_GPU", "0") == "1"
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if one_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import jslpsolver_b200 as J
     from helpers import strip_timeouts
     from oracle import ref_model
@@ -53,7 +61,7 @@ def main():
             same = same and gt.branchAndCutIterations == osol.state.bncIterations
             same = same and bool(np.array_equal(gt.matrix2d(), osol.tableau.matrix()))
             same = same and sol.evaluation == osol.evaluation
-            flag = torch.tensor([1 if same else 0], device="cuda")
+            flag = torch.tensor([1 if same else 0], device="cpu" if one_gpu else "cuda")
             if world > 1:
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ok = bool(flag.item())

@@ -24,10 +24,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    one_gpu = os.environ.get("DIST_ONE_GPU", "0") == "1"  # all ranks on cuda:0 over gloo (logic check only)
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if one_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import jslpsolver_b200 as J
     from jslpsolver_b200 import problems
     from helpers import strip_timeouts
@@ -78,7 +84,9 @@ def main():
                        "node_lps": b.nodes_evaluated, "pivots": b.pivots, "launches": b.kernel_launches,
                        "node_lps_per_s": b.nodes_evaluated * world / (b.gpu_ms * 1e-3) if world == 1 else None,
                        "committed_nodes_per_s": b.iterations / (b.gpu_ms * 1e-3), "result": sol.evaluation,
-                       "host_eval_ms": b.host_eval_ms, "host_commit_ms": b.host_commit_ms}
+                       "host_eval_ms": b.host_eval_ms, "host_commit_ms": b.host_commit_ms,
+                       "host_root_ms": b.host_root_ms, "host_final_ms": b.host_final_ms,
+                       "node_kernel_ms": b.node_kernel_ms}
                 if best is None or rec["gpu_ms"] < best["gpu_ms"]:
                     best = rec
             if rank == 0:
