@@ -663,7 +663,7 @@ static int run_lp_resident(jslp_tab *t, int check_cycles, jslp_lp_status *out, b
     cudaStream_t s = ctx->stream;
     int Ws = 0;
     const size_t smem = node_smem_bytes(t->H, t->W, &Ws);
-    if (t->nOpt > 0 || smem > (size_t)ctx->max_smem_optin - 2048) return JSLP_OK;
+    if (t->nOpt > 0 || smem > (size_t)ctx->max_smem_optin - 4096) return JSLP_OK;
     int rc = ensure_snapshot(t, 0);
     if (rc) return rc;
     const Snapshot &snap = t->snaps[0];

@@ -129,11 +129,11 @@ static size_t node_smem_bytes(int Hcap, int W, int *Ws_out) {
     const int Ws = (W & 1) ? W : W + 1;  // odd row stride: conflict-free column walks
     if (Ws_out) *Ws_out = Ws;
     return sizeof(double) * ((size_t)Hcap * Ws + 2 * (size_t)Ws + Hcap) + sizeof(CutDev) * (size_t)Hcap +
-           sizeof(int) * ((size_t)Hcap + W) + 16;
+           sizeof(int) * (2 * (size_t)Hcap + W) + 16;
 }
 
 static bool resident_fits(const jslp_tab *t, int Hcap) {
-    return t->nOpt == 0 && node_smem_bytes(Hcap, t->W, nullptr) <= (size_t)t->ctx->max_smem_optin - 2048;
+    return t->nOpt == 0 && node_smem_bytes(Hcap, t->W, nullptr) <= (size_t)t->ctx->max_smem_optin - 4096;
 }
 
 // Evaluates nodes[0..n) with one CTA each (k_node_batch).  Nodes whose log shows a cycle or that

@@ -5,8 +5,9 @@
 // (cutting-strategies.ts:36-71), run phase 1 / phase 2 to completion (simplex.ts:14-325) and
 // report the summary the frontier needs (evaluation, isIntegral, most fractional variable;
 // mip-utils.ts:43-61,100-126).  A launch evaluates a whole batch of open nodes, one CTA each:
-// this is what makes the node frontier GPU-resident.  Selection code is the same template as the
-// HBM path (cta_select<false>), so both paths obey identical tie-break rules.
+// this is what makes the node frontier GPU-resident.  Selection is done by ONE warp with shuffle
+// reductions (no CTA barrier): the same rules as cta_select, restated at warp scope; the parity tests
+// run every fixture through both paths.
 #pragma once
 #include "jslp_kernels.cuh"
 
@@ -54,12 +55,61 @@ __device__ __forceinline__ long long globaltimer_ns() {
     return t;
 }
 
+// ---- warp-level selection ----------------------------------------------------------------------
+// In the resident kernel one warp decides every pivot with shuffles only: for tableaux this small a
+// CTA-wide reduction (two barriers + a shared-memory hop) costs more than the scan it reduces.
+template <bool IS_MIN>
+__device__ __forceinline__ VI warp_reduce_vi(VI x) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        VI y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+        if (better<IS_MIN>(y, x)) x = y;
+    }
+    return x;
+}
+
+// Phase-2 pricing of the cost row (simplex.ts:140-219 without optional objectives): first batch with
+// an improving column, arg-max inside it, lowest column on ties.  Returns the column (0 = none).
+__device__ __forceinline__ int warp_price(const TabDev &T, const double *cost, const int *vcol, int W, int lane, int *neg_out) {
+    const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
+    const bool has_unres = T.unres != nullptr;
+    PriceAcc acc;
+    price_init(acc, T.prec);
+    for (int c = 1 + lane; c < W; c += 32) {
+        const double nc = cost[c];
+        int label = -1;
+        if (has_unres && nc < 0) label = vcol[c];
+        price_consider(T, acc, c, nc, label, bsz);
+    }
+    int b = acc.myb, i = acc.x.i, neg = acc.myneg;
+    double v = acc.x.v;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int yb = __shfl_xor_sync(0xffffffffu, b, o), yi = __shfl_xor_sync(0xffffffffu, i, o);
+        const int yn = __shfl_xor_sync(0xffffffffu, neg, o);
+        const double yv = __shfl_xor_sync(0xffffffffu, v, o);
+        if (yb < b || (yb == b && (yv > v || (yv == v && yi < i)))) { b = yb; v = yv; i = yi; neg = yn; }
+    }
+    *neg_out = b == INT_MAX ? 0 : neg;
+    return b == INT_MAX ? 0 : i;
+}
+
+struct NodePivot {   // warp 0 -> CTA
+    int go, r, c, flush;
+    double q;
+};
+
 __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, NodeBatchDev nb) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ TabDev T;
-    __shared__ Rec rec;
     __shared__ SelSmem sel;
     __shared__ MipOut mip;
+    __shared__ NodePivot piv;
+    __shared__ int s_spare;
+    __shared__ int s_fin[8];   // status, p1, p2, log_n, overflow, unbounded_var
+    __shared__ double s_eval;
     const int tid = threadIdx.x, NT = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
     const int node = blockIdx.x;
@@ -69,18 +119,22 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
     const int c0 = nb.cut_off[node], nc = nb.cut_off[node + 1] - c0;
     const int H0 = nb.H0, Ws = nb.Ws;
 
+    // rows live in Hcap + 1 slots: the normalised pivot row is written to the spare slot and the slot
+    // table is swapped, so nobody waits for the old pivot row to be overwritten in place
     double *Ms = reinterpret_cast<double *>(smraw);
-    double *prow = Ms + (size_t)nb.Hcap * Ws;
-    double *frow = prow + Ws;
-    double *pcol = frow + Ws;
-    CutDev *cutS = reinterpret_cast<CutDev *>(pcol + nb.Hcap);
+    double *frow = Ms + (size_t)(nb.Hcap + 1) * Ws;
+    double *rhs = frow + Ws;                         // Hcap entries, final RHS column for the MIP scan
+    CutDev *cutS = reinterpret_cast<CutDev *>(rhs + nb.Hcap);
     int *vrow = reinterpret_cast<int *>(cutS + (nb.Hcap - H0));
+    int *slot = vrow + nb.Hcap;
     if (tid == 0) {
         T = *Tp;
-        T.vcol = vrow + nb.Hcap;
+        T.vcol = slot + nb.Hcap;
+        s_spare = nb.Hcap;
     }
     __syncthreads();
     const int W = T.W;
+    const double prec = T.prec;
     int *vcol = T.vcol;
 
     // restore(): root snapshot -> shared memory, eight loads in flight per thread before their stores
@@ -105,6 +159,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
     }
     for (int r = tid; r < H0; r += NT) vrow[r] = __ldg(nb.root_vrow + r);
     for (int c = tid; c < W; c += NT) vcol[c] = __ldg(nb.root_vcol + c);
+    for (int r = tid; r < nb.Hcap; r += NT) slot[r] = r;
     for (int h = tid; h < nc; h += NT) cutS[h] = nb.cuts[c0 + h];
     const int Hn = H0 + nc;
     __syncthreads();
@@ -127,46 +182,120 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         }
         if (lane == 0) vrow[H0 + h] = nb.first_index + h;
     }
-    if (tid == 0) {
-        T.M = Ms; T.vrow = vrow; T.prow = prow; T.pcol = pcol;
-        T.stride = Ws; T.H = Hn; T.rowcap = nb.Hcap;
-        T.plog = nb.logs + (size_t)node * nb.log_cap;
-        T.plog_cap = nb.log_cap;
-        rec.status = ST_RUNNING; rec.phase = 1; rec.has_pivot = 0; rec.r = rec.c = 0; rec.is_neg = 0;
-        rec.flush = 0; rec.done = 0; rec.p1 = rec.p2 = 0; rec.stop_at = -1; rec.log_n = 0;
-        rec.unbounded_var = -1; rec.only_phase = 0; rec.ticket = 0; rec.q = 0; rec.eval_raw = 0;
-    }
     __syncthreads();
 
-    int overflow = 0;
+    // warp 0's registers: the solve state
+    int phase = 1, p1 = 0, p2 = 0, log_n = 0, status = ST_RUNNING, overflow = 0, unb = -1;
+    int next_c = -1, next_neg = 0;      // look-ahead pricing of the updated cost row (-1 = not priced)
+    int4 *plog = nb.logs + (size_t)node * nb.log_cap;
+    const bool has_unres = T.unres != nullptr;
+
     for (;;) {
-        cta_select<false>(T, &rec, sel);
-        __syncthreads();
-        if (!rec.has_pivot) break;
-        if (rec.done >= nb.max_pivots || rec.log_n > nb.log_cap) { overflow = 1; break; }
-        const int rstar = rec.r, cstar = rec.c, flush = rec.flush, phase = rec.phase;
-        const double q = rec.q;
-        for (int c = tid; c < W; c += NT) {  // simplex.ts:352-364 (+ lazy flush 380-382)
-            const double v = prow[c];
-            double f = nz16(v) ? v / q : 0.0;
-            if (c == cstar) f = 1.0 / q;
-            if (flush && !nz16(f) && f != 0.0) f = 0.0;
-            frow[c] = f;
+        if (warp == 0) {
+            // ---- select (phase 1: simplex.ts:38-76, phase 2: 129-303), warp-wide ----------------
+            const double *cost = Ms + (size_t)slot[0] * Ws;
+            int rstar = -1, cstar = -1, isneg = 0, go = 1;
+            if (p1 + p2 >= nb.max_pivots || log_n >= nb.log_cap) { overflow = 1; go = 0; }
+            if (go && phase == 1) {
+                VI b = {-prec, INT_MAX};
+                for (int r = 1 + lane; r < Hn; r += 32) {
+                    const double v = Ms[(size_t)slot[r] * Ws];
+                    if (v < b.v) { b.v = v; b.i = r; }
+                }
+                b = warp_reduce_vi<true>(b);
+                if (b.i == INT_MAX) {
+                    phase = 2;  // feasible (simplex.ts:51-54)
+                } else {
+                    rstar = b.i;
+                    const double *lrow = Ms + (size_t)slot[rstar] * Ws;
+                    VI e = {-INFINITY, INT_MAX};
+                    for (int c = 1 + lane; c < W; c += 32) {
+                        const double coef = lrow[c];
+                        if ((has_unres && is_unres(T, vcol[c])) || coef < -prec) {
+                            const double quo = -cost[c] / coef;
+                            if (e.v < quo) { e.v = quo; e.i = c; }
+                        }
+                    }
+                    e = warp_reduce_vi<false>(e);
+                    if (e.i == INT_MAX) { status = ST_INFEASIBLE; go = 0; }  // simplex.ts:73-76
+                    else cstar = e.i;
+                }
+            }
+            int cnt = 0;
+            if (go && rstar < 0) {  // phase 2
+                if (next_c < 0) next_c = warp_price(T, cost, vcol, W, lane, &next_neg);
+                if (next_c == 0) { status = ST_OPTIMAL; go = 0; }  // simplex.ts:265-269
+                else {
+                    cstar = next_c; isneg = next_neg;
+                    // ratio test (simplex.ts:271-296)
+                    VI m = {INFINITY, INT_MAX};
+                    int dmin = INT_MAX;
+                    for (int r = lane; r < Hn; r += 32) {
+                        const double *row = Ms + (size_t)slot[r] * Ws;
+                        const double col = row[cstar], rhsv = row[0];
+                        if (nz16(col)) cnt++;
+                        if (r == 0) continue;
+                        if (-prec < col && col < prec) continue;
+                        if (col > 0 && prec > rhsv && rhsv > -prec) { dmin = min(dmin, r); continue; }
+                        const double quo = isneg ? -rhsv / col : rhsv / col;
+                        if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+                    }
+                    m = warp_reduce_vi<true>(m);
+                    dmin = __reduce_min_sync(0xffffffffu, dmin);
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                    if (dmin != INT_MAX) rstar = dmin;
+                    else if (m.i != INT_MAX) rstar = m.i;
+                    else { status = ST_UNBOUNDED; unb = vcol[cstar]; go = 0; }  // simplex.ts:298-303
+                }
+            } else if (go) {  // phase-1 pivot: count the non-zero pivot-column entries
+                for (int r = lane; r < Hn; r += 32)
+                    if (nz16(Ms[(size_t)slot[r] * Ws + cstar])) cnt++;
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+            }
+            if (go) {
+                const double q = Ms[(size_t)slot[rstar] * Ws + cstar];
+                if (lane == 0) {
+                    const int leaving = vrow[rstar], entering = vcol[cstar];
+                    plog[log_n] = make_int4(rstar | (phase == 2 ? (1 << 30) : 0), cstar, leaving, entering);
+                    vrow[rstar] = entering;  // simplex.ts:339-349
+                    vcol[cstar] = leaving;
+                    piv.go = 1; piv.r = rstar; piv.c = cstar; piv.q = q;
+                    piv.flush = (cnt - (nz16(q) ? 1 : 0)) > 0;
+                }
+                log_n++;
+                if (phase == 1) p1++; else p2++;
+                next_c = -1;
+            } else if (lane == 0) {
+                piv.go = 0;
+                s_fin[0] = status; s_fin[1] = p1; s_fin[2] = p2; s_fin[3] = log_n; s_fin[4] = overflow; s_fin[5] = unb;
+                s_eval = cost[0];
+            }
         }
         __syncthreads();
-        if (tid == 0) {  // every thread has read the record before the barrier above
-            rec.done += 1;
-            if (phase == 1) rec.p1 += 1; else rec.p2 += 1;
-            rec.has_pivot = 0;
+        if (!piv.go) break;
+        const int rstar = piv.r, cstar = piv.c, flush = piv.flush, spare = s_spare;
+        const double q = piv.q;
+        {
+            const double *praw = Ms + (size_t)slot[rstar] * Ws;
+            for (int c = tid; c < W; c += NT) {  // simplex.ts:352-364 (+ lazy flush 380-382)
+                const double v = praw[c];
+                double f = nz16(v) ? v / q : 0.0;
+                if (c == cstar) f = 1.0 / q;
+                if (flush && !nz16(f) && f != 0.0) f = 0.0;
+                frow[c] = f;
+            }
         }
+        __syncthreads();
         // simplex.ts:367-391, one row per warp: rows with a zero pivot-column entry cost one test
         for (int r = warp; r < Hn; r += NW) {
-            double *row = Ms + r * Ws;
             if (r == rstar) {
-                for (int c = lane; c < W; c += 32) row[c] = frow[c];
+                double *dst = Ms + (size_t)spare * Ws;
+                for (int c = lane; c < W; c += 32) dst[c] = frow[c];
                 continue;
             }
-            const double coef = pcol[r];
+            double *row = Ms + (size_t)slot[r] * Ws;
+            const double coef = row[cstar];
+            __syncwarp();
             if (nz16(coef)) {
                 for (int c = lane; c < W; c += 32) {
                     if (c == cstar) { row[c] = -coef / q; continue; }
@@ -176,31 +305,47 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
             } else if (coef != 0.0 && lane == 0) {
                 row[cstar] = 0.0;
             }
+            if (r == 0) {  // warp 0: price the updated cost row now, off the critical path
+                __syncwarp();
+                next_c = warp_price(T, row, vcol, W, lane, &next_neg);
+            }
         }
         __syncthreads();
+        if (tid == 0) {
+            const int old = slot[rstar];
+            slot[rstar] = spare;
+            s_spare = old;
+        }
+        __syncwarp();  // warp 0 reads the slot table next; every other warp waits at the next barrier
     }
 
-    if (T.intpos != nullptr) cta_mip_scan(T, &mip, sel.red);
-    else if (tid == 0) { mip.is_integral = 1; mip.var_index = -1; mip.value = 0.0; }
+    // isIntegral / most fractional variable over the final RHS column
+    for (int r = tid; r < Hn; r += NT) rhs[r] = Ms[(size_t)slot[r] * Ws];
+    __syncthreads();
+    if (T.intpos != nullptr) {
+        if (tid == 0) { T.M = rhs; T.stride = 1; T.vrow = vrow; T.H = Hn; }
+        __syncthreads();
+        cta_mip_scan(T, &mip, sel.red);
+    } else if (tid == 0) { mip.is_integral = 1; mip.var_index = -1; mip.value = 0.0; }
     __syncthreads();
     NodeOut *out = nb.out + node;
     {
-        const int nlog = min(min(rec.log_n, nb.log_cap), NODE_LOG_HEAD);
-        for (int k = tid; k < nlog; k += NT) out->log_head[k] = T.plog[k];
+        const int nlog = min(min(s_fin[3], nb.log_cap), NODE_LOG_HEAD);
+        for (int k = tid; k < nlog; k += NT) out->log_head[k] = plog[k];
     }
     if (nb.wb_M != nullptr && node == 0) {
-        for (int i = tid; i < Hn * W; i += NT) {
-            const int r = i / W, c = i - r * W;
-            nb.wb_M[(size_t)r * nb.root_stride + c] = Ms[r * Ws + c];
+        for (int r = warp; r < Hn; r += NW) {
+            const double *row = Ms + (size_t)slot[r] * Ws;
+            for (int c = lane; c < W; c += 32) nb.wb_M[(size_t)r * nb.root_stride + c] = row[c];
         }
         for (int r = tid; r < Hn; r += NT) nb.wb_vrow[r] = vrow[r];
         for (int c = tid; c < W; c += NT) nb.wb_vcol[c] = vcol[c];
     }
     if (tid == 0) {
         NodeResult r;
-        r.status = rec.status; r.p1 = rec.p1; r.p2 = rec.p2; r.log_n = rec.log_n; r.overflow = overflow;
-        r.is_integral = mip.is_integral; r.branch_var = mip.var_index; r.unbounded_var = rec.unbounded_var;
-        r.eval_raw = rec.eval_raw; r.branch_value = mip.value;
+        r.status = s_fin[0]; r.p1 = s_fin[1]; r.p2 = s_fin[2]; r.log_n = s_fin[3]; r.overflow = s_fin[4];
+        r.is_integral = mip.is_integral; r.branch_var = mip.var_index; r.unbounded_var = s_fin[5];
+        r.eval_raw = s_eval; r.branch_value = mip.value;
         r.t_ns = globaltimer_ns() - t_start; r.pad = 0;
         out->r = r;
     }

@@ -29,6 +29,7 @@ def main():
     one_gpu = os.environ.get("DIST_ONE_GPU", "0") == "1"
     if one_gpu:
         local = 0
+        os.environ["JSLP_DEVICE"] = "0"
     torch.cuda.set_device(local)
     if world > 1:
         if one_gpu:
