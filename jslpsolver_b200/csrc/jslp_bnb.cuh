@@ -179,6 +179,15 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
     long long slowest = 0;
     bool need_full = false;
     for (int i = 0; i < n; i++) {
+        if (rb.h_out[i].r.t_ns > slowest) {
+            static const bool dbg = getenv("JSLP_DEBUG") != nullptr;
+            if (dbg && i == n - 1) {}
+        }
+        if (getenv("JSLP_DEBUG")) {
+            const NodeResult &q = rb.h_out[i].r;
+            fprintf(stderr, "node r%d n%d i%d cuts %d piv %d+%d: off %lld restore %lld cuts %lld pivots %lld mip %lld end %lld\n",
+                    (int)ctx->launches, n, i, (int)nodes[i]->cuts.size(), q.p1, q.p2, q.tl[0], q.tl[1], q.tl[2], q.tl[3], q.tl[4], q.t_ns);
+        }
         slowest = std::max(slowest, rb.h_out[i].r.t_ns);
         if (check_cycles && !rb.h_out[i].r.overflow && rb.h_out[i].r.log_n > NODE_LOG_HEAD) need_full = true;
     }

@@ -25,6 +25,7 @@ struct NodeResult {
     double branch_value;
     long long t_ns;   // CTA lifetime by %globaltimer (reporting only)
     long long pad;
+    long long tl[6];  // ns since CTA start: offsets read, restored, cut rows built, pivots done, mip scan done, (unused)
 };
 
 // What a CTA reports: the summary plus the head of its pivot log (enough for the cycle check of
@@ -56,18 +57,36 @@ __device__ __forceinline__ long long globaltimer_ns() {
 }
 
 // ---- warp-level selection ----------------------------------------------------------------------
-// In the resident kernel one warp decides every pivot with shuffles only: for tableaux this small a
-// CTA-wide reduction (two barriers + a shared-memory hop) costs more than the scan it reduces.
+// In the resident kernel one warp decides every pivot.  A lone warp issues a dependent instruction
+// every ~8 cycles, so the reductions avoid shuffle trees: values are mapped to order-preserving
+// integer keys and reduced with redux.sync (three to four REDUX per arg-min instead of five shuffle
+// levels of fp64 compares), and the scans issue their loads and divisions four at a time.
+__device__ __forceinline__ unsigned long long dkey(double v) {  // order-preserving for non-NaN, -0 == +0
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// (value, index) arg-min / arg-max over the warp, lowest index on ties; x.v must not be NaN.
 template <bool IS_MIN>
 __device__ __forceinline__ VI warp_reduce_vi(VI x) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        VI y;
-        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
-        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
-        if (better<IS_MIN>(y, x)) x = y;
+    const unsigned long long k = dkey(x.v);
+    const unsigned int hi = (unsigned int)(k >> 32), lo = (unsigned int)k;
+    unsigned int mhi, mlo;
+    if (IS_MIN) {
+        mhi = __reduce_min_sync(0xffffffffu, hi);
+        mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    } else {
+        mhi = __reduce_max_sync(0xffffffffu, hi);
+        mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
     }
-    return x;
+    VI r;
+    r.i = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? x.i : INT_MAX);
+    r.v = dkey_inv(((unsigned long long)mhi << 32) | mlo);
+    return r;
 }
 
 // Phase-2 pricing of the cost row (simplex.ts:140-219 without optional objectives): first batch with
@@ -77,23 +96,34 @@ __device__ __forceinline__ int warp_price(const TabDev &T, const double *cost, c
     const bool has_unres = T.unres != nullptr;
     PriceAcc acc;
     price_init(acc, T.prec);
-    for (int c = 1 + lane; c < W; c += 32) {
-        const double nc = cost[c];
-        int label = -1;
-        if (has_unres && nc < 0) label = vcol[c];
-        price_consider(T, acc, c, nc, label, bsz);
-    }
-    int b = acc.myb, i = acc.x.i, neg = acc.myneg;
-    double v = acc.x.v;
+    for (int c0 = 1; c0 < W; c0 += 128) {
+        double nc[4];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const int yb = __shfl_xor_sync(0xffffffffu, b, o), yi = __shfl_xor_sync(0xffffffffu, i, o);
-        const int yn = __shfl_xor_sync(0xffffffffu, neg, o);
-        const double yv = __shfl_xor_sync(0xffffffffu, v, o);
-        if (yb < b || (yb == b && (yv > v || (yv == v && yi < i)))) { b = yb; v = yv; i = yi; neg = yn; }
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + lane + 32 * k;
+            nc[k] = c < W ? cost[c] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + lane + 32 * k;
+            if (c >= W) continue;
+            int label = -1;
+            if (has_unres && nc[k] < 0) label = vcol[c];
+            price_consider(T, acc, c, nc[k], label, bsz);
+        }
     }
-    *neg_out = b == INT_MAX ? 0 : neg;
-    return b == INT_MAX ? 0 : i;
+    // lexicographic (batch asc, value desc, column asc)
+    const int mb = __reduce_min_sync(0xffffffffu, acc.myb);
+    if (mb == INT_MAX) { *neg_out = 0; return 0; }
+    const bool in = acc.myb == mb;
+    const unsigned long long k = dkey(acc.x.v);
+    const unsigned int hi = (unsigned int)(k >> 32), lo = (unsigned int)k;
+    const unsigned int mhi = __reduce_max_sync(0xffffffffu, in ? hi : 0u);
+    const unsigned int mlo = __reduce_max_sync(0xffffffffu, (in && hi == mhi) ? lo : 0u);
+    const bool win = in && hi == mhi && lo == mlo;
+    const int col = __reduce_min_sync(0xffffffffu, win ? acc.x.i : INT_MAX);
+    *neg_out = __reduce_max_sync(0xffffffffu, (win && acc.x.i == col) ? acc.myneg : 0);
+    return col;
 }
 
 struct NodePivot {   // warp 0 -> CTA
@@ -118,6 +148,8 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
     // issued first, used after the restore: these two may cross PCIe
     const int c0 = nb.cut_off[node], nc = nb.cut_off[node + 1] - c0;
     const int H0 = nb.H0, Ws = nb.Ws;
+    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl4 = 0;
+    if (tid == 0 && nc >= 0) tl0 = globaltimer_ns() - t_start;
 
     // rows live in Hcap + 1 slots: the normalised pivot row is written to the spare slot and the slot
     // table is swapped, so nobody waits for the old pivot row to be overwritten in place
@@ -163,6 +195,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
     for (int h = tid; h < nc; h += NT) cutS[h] = nb.cuts[c0 + h];
     const int Hn = H0 + nc;
     __syncthreads();
+    if (tid == 0) tl1 = globaltimer_ns() - t_start;
     // addCutConstraints(): every cut row is expressed in the ROOT basis, so the rows are independent:
     // one warp per cut, no CTA barrier inside
     for (int h = warp; h < nc; h += NW) {
@@ -183,6 +216,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         if (lane == 0) vrow[H0 + h] = nb.first_index + h;
     }
     __syncthreads();
+    if (tid == 0) tl2 = globaltimer_ns() - t_start;
 
     // warp 0's registers: the solve state
     int phase = 1, p1 = 0, p2 = 0, log_n = 0, status = ST_RUNNING, overflow = 0, unb = -1;
@@ -190,6 +224,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
     int4 *plog = nb.logs + (size_t)node * nb.log_cap;
     const bool has_unres = T.unres != nullptr;
 
+    double *pcol = rhs;  // old pivot-column entries of the pivot in flight (the RHS copy is only made at the end)
     for (;;) {
         if (warp == 0) {
             // ---- select (phase 1: simplex.ts:38-76, phase 2: 129-303), warp-wide ----------------
@@ -198,9 +233,18 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
             if (p1 + p2 >= nb.max_pivots || log_n >= nb.log_cap) { overflow = 1; go = 0; }
             if (go && phase == 1) {
                 VI b = {-prec, INT_MAX};
-                for (int r = 1 + lane; r < Hn; r += 32) {
-                    const double v = Ms[(size_t)slot[r] * Ws];
-                    if (v < b.v) { b.v = v; b.i = r; }
+                for (int r0 = 1; r0 < Hn; r0 += 128) {
+                    double v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int r = r0 + lane + 32 * k;
+                        v[k] = r < Hn ? Ms[(size_t)slot[r] * Ws] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int r = r0 + lane + 32 * k;
+                        if (r < Hn && v[k] < b.v) { b.v = v[k]; b.i = r; }
+                    }
                 }
                 b = warp_reduce_vi<true>(b);
                 if (b.i == INT_MAX) {
@@ -209,12 +253,20 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
                     rstar = b.i;
                     const double *lrow = Ms + (size_t)slot[rstar] * Ws;
                     VI e = {-INFINITY, INT_MAX};
-                    for (int c = 1 + lane; c < W; c += 32) {
-                        const double coef = lrow[c];
-                        if ((has_unres && is_unres(T, vcol[c])) || coef < -prec) {
-                            const double quo = -cost[c] / coef;
-                            if (e.v < quo) { e.v = quo; e.i = c; }
+                    for (int c0 = 1; c0 < W; c0 += 128) {  // four divisions in flight per lane
+                        double quo[4];
+                        bool ok[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int c = c0 + lane + 32 * k;
+                            const double coef = c < W ? lrow[c] : 0.0;
+                            const double cv = c < W ? cost[c] : 0.0;
+                            ok[k] = c < W && ((has_unres && is_unres(T, vcol[c])) || coef < -prec);
+                            quo[k] = -cv / coef;
                         }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (ok[k] && e.v < quo[k]) { e.v = quo[k]; e.i = c0 + lane + 32 * k; }
                     }
                     e = warp_reduce_vi<false>(e);
                     if (e.i == INT_MAX) { status = ST_INFEASIBLE; go = 0; }  // simplex.ts:73-76
@@ -230,22 +282,34 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
                     // ratio test (simplex.ts:271-296)
                     VI m = {INFINITY, INT_MAX};
                     int dmin = INT_MAX;
-                    for (int r = lane; r < Hn; r += 32) {
-                        const double *row = Ms + (size_t)slot[r] * Ws;
-                        const double col = row[cstar], rhsv = row[0];
-                        if (nz16(col)) cnt++;
-                        if (r == 0) continue;
-                        if (-prec < col && col < prec) continue;
-                        if (col > 0 && prec > rhsv && rhsv > -prec) { dmin = min(dmin, r); continue; }
-                        const double quo = isneg ? -rhsv / col : rhsv / col;
-                        if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+                    for (int r0 = 0; r0 < Hn; r0 += 128) {
+                        double col[4], rv[4], quo[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int r = r0 + lane + 32 * k;
+                            const double *row = Ms + (size_t)slot[r < Hn ? r : 0] * Ws;
+                            col[k] = row[cstar]; rv[k] = row[0];
+                            quo[k] = isneg ? -rv[k] / col[k] : rv[k] / col[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int r = r0 + lane + 32 * k;
+                            if (r >= Hn) continue;
+                            if (nz16(col[k])) cnt++;
+                            if (r == 0) continue;
+                            if (-prec < col[k] && col[k] < prec) continue;
+                            if (col[k] > 0 && prec > rv[k] && rv[k] > -prec) { dmin = min(dmin, r); continue; }
+                            if (quo[k] > prec && m.v > quo[k]) { m.v = quo[k]; m.i = r; }
+                        }
                     }
-                    m = warp_reduce_vi<true>(m);
                     dmin = __reduce_min_sync(0xffffffffu, dmin);
                     cnt = __reduce_add_sync(0xffffffffu, cnt);
                     if (dmin != INT_MAX) rstar = dmin;
-                    else if (m.i != INT_MAX) rstar = m.i;
-                    else { status = ST_UNBOUNDED; unb = vcol[cstar]; go = 0; }  // simplex.ts:298-303
+                    else {
+                        m = warp_reduce_vi<true>(m);
+                        if (m.i != INT_MAX) rstar = m.i;
+                        else { status = ST_UNBOUNDED; unb = vcol[cstar]; go = 0; }  // simplex.ts:298-303
+                    }
                 }
             } else if (go) {  // phase-1 pivot: count the non-zero pivot-column entries
                 for (int r = lane; r < Hn; r += 32)
@@ -275,40 +339,69 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         if (!piv.go) break;
         const int rstar = piv.r, cstar = piv.c, flush = piv.flush, spare = s_spare;
         const double q = piv.q;
-        {
+        // Both division passes at once: the lower half of the CTA normalises the pivot row
+        // (simplex.ts:352-364 + lazy flush 380-382), the upper half rewrites the pivot column
+        // (simplex.ts:372-374,386-388) after staging its old entries for the row updates.
+        if (tid < NT / 2) {
             const double *praw = Ms + (size_t)slot[rstar] * Ws;
-            for (int c = tid; c < W; c += NT) {  // simplex.ts:352-364 (+ lazy flush 380-382)
+            for (int c = tid; c < W; c += NT / 2) {
                 const double v = praw[c];
                 double f = nz16(v) ? v / q : 0.0;
                 if (c == cstar) f = 1.0 / q;
                 if (flush && !nz16(f) && f != 0.0) f = 0.0;
                 frow[c] = f;
             }
+        } else {
+            for (int r = tid - NT / 2; r < Hn; r += NT / 2) {
+                if (r == rstar) { pcol[r] = 0.0; continue; }
+                double *e = Ms + (size_t)slot[r] * Ws + cstar;
+                const double coef = *e;
+                pcol[r] = coef;
+                if (nz16(coef)) *e = -coef / q;
+                else if (coef != 0.0) *e = 0.0;
+            }
         }
         __syncthreads();
-        // simplex.ts:367-391, one row per warp: rows with a zero pivot-column entry cost one test
-        for (int r = warp; r < Hn; r += NW) {
-            if (r == rstar) {
-                double *dst = Ms + (size_t)spare * Ws;
-                for (int c = lane; c < W; c += 32) dst[c] = frow[c];
-                continue;
+        // simplex.ts:367-391: warp 0 owns the cost row and then prices it (look-ahead, off the other
+        // warps' critical path); rows 1.. are dealt over the other warps.  A lane's columns are the
+        // same for every row, so its share of the normalised pivot row lives in registers.
+        for (int cb = 0; cb < W; cb += 128) {
+            double fr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = cb + lane + 32 * k;
+                fr[k] = c < W ? frow[c] : 0.0;
             }
-            double *row = Ms + (size_t)slot[r] * Ws;
-            const double coef = row[cstar];
-            __syncwarp();
-            if (nz16(coef)) {
-                for (int c = lane; c < W; c += 32) {
-                    if (c == cstar) { row[c] = -coef / q; continue; }
-                    const double v0 = frow[c];
-                    if (nz16(v0)) row[c] = __dsub_rn(row[c], __dmul_rn(coef, v0));
+            const int rfirst = warp == 0 ? 0 : warp, rstep = warp == 0 ? Hn : NW - 1;
+            for (int r = rfirst; r < Hn; r += rstep) {
+                if (r == rstar) {
+                    double *dst = Ms + (size_t)spare * Ws;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int c = cb + lane + 32 * k;
+                        if (c < W) dst[c] = fr[k];
+                    }
+                    continue;
                 }
-            } else if (coef != 0.0 && lane == 0) {
-                row[cstar] = 0.0;
+                const double coef = pcol[r];
+                if (!nz16(coef)) continue;
+                double *row = Ms + (size_t)slot[r] * Ws;
+                double v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = cb + lane + 32 * k;
+                    v[k] = c < W ? row[c] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = cb + lane + 32 * k;
+                    if (c < W && c != cstar && nz16(fr[k])) row[c] = __dsub_rn(v[k], __dmul_rn(coef, fr[k]));
+                }
             }
-            if (r == 0) {  // warp 0: price the updated cost row now, off the critical path
-                __syncwarp();
-                next_c = warp_price(T, row, vcol, W, lane, &next_neg);
-            }
+        }
+        if (warp == 0) {
+            __syncwarp();
+            next_c = warp_price(T, Ms + (size_t)slot[0] * Ws, vcol, W, lane, &next_neg);
         }
         __syncthreads();
         if (tid == 0) {
@@ -319,6 +412,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         __syncwarp();  // warp 0 reads the slot table next; every other warp waits at the next barrier
     }
 
+    if (tid == 0) tl3 = globaltimer_ns() - t_start;
     // isIntegral / most fractional variable over the final RHS column
     for (int r = tid; r < Hn; r += NT) rhs[r] = Ms[(size_t)slot[r] * Ws];
     __syncthreads();
@@ -328,6 +422,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         cta_mip_scan(T, &mip, sel.red);
     } else if (tid == 0) { mip.is_integral = 1; mip.var_index = -1; mip.value = 0.0; }
     __syncthreads();
+    if (tid == 0) tl4 = globaltimer_ns() - t_start;
     NodeOut *out = nb.out + node;
     {
         const int nlog = min(min(s_fin[3], nb.log_cap), NODE_LOG_HEAD);
@@ -347,6 +442,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         r.is_integral = mip.is_integral; r.branch_var = mip.var_index; r.unbounded_var = s_fin[5];
         r.eval_raw = s_eval; r.branch_value = mip.value;
         r.t_ns = globaltimer_ns() - t_start; r.pad = 0;
+        r.tl[0] = tl0; r.tl[1] = tl1; r.tl[2] = tl2; r.tl[3] = tl3; r.tl[4] = tl4; r.tl[5] = 0;
         out->r = r;
     }
 }

@@ -51,6 +51,7 @@ def main():
                  (f"knapsack {nk} binaries x {mk} constraints (root {nk + mk + 1}x{nk + 1}), first {knap_nodes} nodes",
                   knap, knap_nodes)]
     widths = [int(x) for x in os.environ.get("SPEC", "1,8,32,128").split(",")]
+    spin = torch.zeros(1 << 26, device="cuda")
     for name, model, max_nodes in workloads:
         # the knapsack root LP alone is ~85k pivots of 25 MB: minutes on one CPU core (measured in the
         # build container: 159 s for root + 19 nodes); only the small workload is re-timed here
@@ -69,12 +70,17 @@ def main():
             inst.max_nodes = max_nodes
             inst.tableau.distributed = world > 1
             best = None
-            for rep in range(3):
+            for rep in range(int(os.environ.get("REPS", "5"))):
                 inst = J.Model().loadJson(model)
                 inst.max_nodes = max_nodes
                 inst.tableau.distributed = world > 1
                 inst.tableau.max_spec_batch = K
-                torch.cuda.synchronize()
+                # the idle B200 sits at 120 MHz: keep the SMs busy right up to the timed solve so the
+                # clock governor has ramped (a 20 ms solve of ~100 us kernels never ramps it by itself)
+                t_w = time.perf_counter()
+                while time.perf_counter() - t_w < float(os.environ.get("SPIN_S", "0.4")):
+                    spin.add_(1.0)
+                    torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 sol = inst.solve()
                 torch.cuda.synchronize()
