@@ -126,9 +126,9 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
 }
 
 static size_t node_smem_bytes(int Hcap, int W, int *Ws_out) {
-    const int Ws = (W & 1) ? W : W + 1;  // odd row stride: conflict-free column walks
+    const int Ws = (W + 1) & ~1;  // even row stride: 16-byte aligned rows (TMA restore)
     if (Ws_out) *Ws_out = Ws;
-    return sizeof(double) * ((size_t)Hcap * Ws + 2 * (size_t)Ws + Hcap) + sizeof(CutDev) * (size_t)Hcap +
+    return sizeof(double) * ((size_t)Hcap * Ws + 2 * (size_t)Ws + Hcap + 1) + sizeof(CutDev) * (size_t)Hcap +
            sizeof(int) * (2 * (size_t)Hcap + W) + 16;
 }
 
@@ -168,6 +168,10 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
     nb.cuts = rb.dv_cuts; nb.cut_off = rb.dv_off; nb.out = rb.dv_out; nb.logs = rb.d_logs;
     nb.H0 = t->saved.H; nb.root_stride = t->stride; nb.first_index = t->saved.lastElementIndex;
     nb.Hcap = Hcap; nb.Ws = Ws; nb.log_cap = log_cap; nb.max_pivots = 100000;
+    if (n <= NODE_INLINE_OFF) {
+        nb.n_inline = n;
+        for (int i = 0; i <= n; i++) nb.cut_off_inline[i] = rb.h_off[i];
+    }
     if ((int)smem > rb.smem_set) {
         CK(cudaFuncSetAttribute(k_node_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rb.smem_set = (int)smem;
@@ -185,8 +189,8 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
         }
         if (getenv("JSLP_DEBUG")) {
             const NodeResult &q = rb.h_out[i].r;
-            fprintf(stderr, "node r%d n%d i%d cuts %d piv %d+%d: off %lld restore %lld cuts %lld pivots %lld mip %lld end %lld\n",
-                    (int)ctx->launches, n, i, (int)nodes[i]->cuts.size(), q.p1, q.p2, q.tl[0], q.tl[1], q.tl[2], q.tl[3], q.tl[4], q.t_ns);
+            fprintf(stderr, "node r%d n%d i%d cuts %d piv %d+%d: off %lld restore %lld cuts %lld pivots %lld mip %lld end %lld cy %lld %lld %lld %lld %lld %lld\n",
+                    (int)ctx->launches, n, i, (int)nodes[i]->cuts.size(), q.p1, q.p2, q.tl[0], q.tl[1], q.tl[2], q.tl[3], q.tl[4], q.t_ns, q.cy[0], q.cy[1], q.cy[2], q.cy[3], q.cy[4], q.cy[5]);
         }
         slowest = std::max(slowest, rb.h_out[i].r.t_ns);
         if (check_cycles && !rb.h_out[i].r.overflow && rb.h_out[i].r.log_n > NODE_LOG_HEAD) need_full = true;

@@ -25,6 +25,7 @@ struct NodeResult {
     double branch_value;
     long long t_ns;   // CTA lifetime by %globaltimer (reporting only)
     long long pad;
+    long long cy[6];  // warp-0 cycles: select, barrier A, division passes, row update, look-ahead pricing, barrier B
     long long tl[6];  // ns since CTA start: offsets read, restored, cut rows built, pivots done, mip scan done, (unused)
 };
 
@@ -36,6 +37,7 @@ struct NodeOut {
     int4 log_head[NODE_LOG_HEAD];
 };
 
+constexpr int NODE_INLINE_OFF = 64;
 struct NodeBatchDev {
     const double *rootM;   // root snapshot, row stride = root_stride
     const int *root_vrow, *root_vcol;
@@ -46,6 +48,8 @@ struct NodeBatchDev {
     double *wb_M;          // optional write-back of node 0's final tableau (stride = root_stride)
     int *wb_vrow, *wb_vcol;
     int H0, root_stride, first_index, Hcap, Ws, log_cap, max_pivots;
+    int n_inline;          // > 0: cut_off_inline holds the n_inline + 1 offsets (saves a PCIe round trip)
+    int cut_off_inline[NODE_INLINE_OFF + 1];
 };
 
 constexpr int NODE_THREADS = 256;
@@ -130,70 +134,70 @@ struct NodePivot {   // warp 0 -> CTA
     int go, r, c, flush;
     double q;
 };
+struct NodeScan {    // warp 0 -> CTA: which division scan to run (1 = phase-1 column scan of row r, 2 = ratio test of column c)
+    int mode, r, c, neg;
+};
+struct NodePart {    // per-warp partial results of a scan
+    double v[8];
+    int i[8], d[8], n[8];
+};
 
-__global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, NodeBatchDev nb) {
+__global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, const __grid_constant__ NodeBatchDev nb) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ TabDev T;
     __shared__ SelSmem sel;
     __shared__ MipOut mip;
     __shared__ NodePivot piv;
+    __shared__ NodeScan sc;
+    __shared__ NodePart part;
     __shared__ int s_spare;
     __shared__ int s_fin[8];   // status, p1, p2, log_n, overflow, unbounded_var
     __shared__ double s_eval;
+    __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x, NT = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
     const int node = blockIdx.x;
     long long t_start = 0;
     if (tid == 0) t_start = globaltimer_ns();
-    // issued first, used after the restore: these two may cross PCIe
-    const int c0 = nb.cut_off[node], nc = nb.cut_off[node + 1] - c0;
     const int H0 = nb.H0, Ws = nb.Ws;
-    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl4 = 0;
-    if (tid == 0 && nc >= 0) tl0 = globaltimer_ns() - t_start;
 
     // rows live in Hcap + 1 slots: the normalised pivot row is written to the spare slot and the slot
-    // table is swapped, so nobody waits for the old pivot row to be overwritten in place
+    // table is swapped, so nobody waits for the old pivot row to be overwritten in place.  Ws is even:
+    // rows are 16-byte aligned, which is what lets TMA restore them.
     double *Ms = reinterpret_cast<double *>(smraw);
     double *frow = Ms + (size_t)(nb.Hcap + 1) * Ws;
-    double *rhs = frow + Ws;                         // Hcap entries, final RHS column for the MIP scan
-    CutDev *cutS = reinterpret_cast<CutDev *>(rhs + nb.Hcap);
+    double *rhs = frow + Ws;                         // Hcap entries: pivot-column staging, final RHS column
+    CutDev *cutS = reinterpret_cast<CutDev *>(rhs + nb.Hcap + (nb.Hcap & 1));
     int *vrow = reinterpret_cast<int *>(cutS + (nb.Hcap - H0));
     int *slot = vrow + nb.Hcap;
     if (tid == 0) {
         T = *Tp;
         T.vcol = slot + nb.Hcap;
         s_spare = nb.Hcap;
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
     }
     __syncthreads();
+    // restore(): root snapshot -> shared memory, one TMA bulk copy per row (backup.ts:53-105)
+    if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)(H0 * Ws * sizeof(double)));
+    __syncthreads();
+    for (int r = tid; r < H0; r += NT)
+        tma_bulk_g2s(Ms + (size_t)r * Ws, nb.rootM + (size_t)r * nb.root_stride, (uint32_t)(Ws * sizeof(double)), &s_bar);
+    // the cut list may live in mapped host memory: one PCIe round trip, overlapped with the restore
+    int c0, nc;
+    if (nb.n_inline > 0) { c0 = nb.cut_off_inline[node]; nc = nb.cut_off_inline[node + 1] - c0; }
+    else { c0 = nb.cut_off[node]; nc = nb.cut_off[node + 1] - c0; }
+    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl4 = 0;
     const int W = T.W;
     const double prec = T.prec;
     int *vcol = T.vcol;
-
-    // restore(): root snapshot -> shared memory, eight loads in flight per thread before their stores
-    {
-        int r = 0, c = tid;
-        while (c >= W) { c -= W; r++; }
-        const int total = H0 * W;
-        for (int i0 = tid; i0 < total; i0 += 8 * NT) {
-            double v[8];
-            int rr[8], cc[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                rr[k] = r; cc[k] = c;
-                v[k] = (i0 + k * NT < total) ? __ldg(nb.rootM + (size_t)r * nb.root_stride + c) : 0.0;
-                c += NT;
-                while (c >= W) { c -= W; r++; }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (i0 + k * NT < total) Ms[rr[k] * Ws + cc[k]] = v[k];
-        }
-    }
+    for (int h = tid; h < nc; h += NT) cutS[h] = nb.cuts[c0 + h];
     for (int r = tid; r < H0; r += NT) vrow[r] = __ldg(nb.root_vrow + r);
     for (int c = tid; c < W; c += NT) vcol[c] = __ldg(nb.root_vcol + c);
     for (int r = tid; r < nb.Hcap; r += NT) slot[r] = r;
-    for (int h = tid; h < nc; h += NT) cutS[h] = nb.cuts[c0 + h];
     const int Hn = H0 + nc;
+    if (tid == 0) tl0 = globaltimer_ns() - t_start;
+    mbar_wait(&s_bar, 0);
     __syncthreads();
     if (tid == 0) tl1 = globaltimer_ns() - t_start;
     // addCutConstraints(): every cut row is expressed in the ROOT basis, so the rows are independent:
@@ -221,15 +225,23 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
     // warp 0's registers: the solve state
     int phase = 1, p1 = 0, p2 = 0, log_n = 0, status = ST_RUNNING, overflow = 0, unb = -1;
     int next_c = -1, next_neg = 0;      // look-ahead pricing of the updated cost row (-1 = not priced)
+    int rstar = -1, cstar = -1, isneg = 0;
     int4 *plog = nb.logs + (size_t)node * nb.log_cap;
     const bool has_unres = T.unres != nullptr;
-
+    long long cy[6] = {0, 0, 0, 0, 0, 0}, cprev = clock64();
+#define NODE_CY(k) do { const long long cnow = clock64(); cy[k] += cnow - cprev; cprev = cnow; } while (0)
     double *pcol = rhs;  // old pivot-column entries of the pivot in flight (the RHS copy is only made at the end)
+
+    // One pivot = five CTA barriers.  fp64 division has a latency of several hundred cycles and does not
+    // interleave (each one carries a slow-path branch), so every pass that divides is spread over the
+    // whole CTA, one element per thread: (S2) the phase-1 column scan / the ratio test, (D) pivot-row
+    // normalisation + pivot-column rewrite.  The cheap decisions (S1, S3) stay in warp 0's registers.
     for (;;) {
+        // ---- S1 (warp 0): leaving row (phase 1: simplex.ts:38-54) or entering column (phase 2: 129-269)
         if (warp == 0) {
-            // ---- select (phase 1: simplex.ts:38-76, phase 2: 129-303), warp-wide ----------------
             const double *cost = Ms + (size_t)slot[0] * Ws;
-            int rstar = -1, cstar = -1, isneg = 0, go = 1;
+            int go = 1;
+            rstar = -1; cstar = -1; isneg = 0;
             if (p1 + p2 >= nb.max_pivots || log_n >= nb.log_cap) { overflow = 1; go = 0; }
             if (go && phase == 1) {
                 VI b = {-prec, INT_MAX};
@@ -247,74 +259,88 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
                     }
                 }
                 b = warp_reduce_vi<true>(b);
-                if (b.i == INT_MAX) {
-                    phase = 2;  // feasible (simplex.ts:51-54)
-                } else {
-                    rstar = b.i;
-                    const double *lrow = Ms + (size_t)slot[rstar] * Ws;
-                    VI e = {-INFINITY, INT_MAX};
-                    for (int c0 = 1; c0 < W; c0 += 128) {  // four divisions in flight per lane
-                        double quo[4];
-                        bool ok[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int c = c0 + lane + 32 * k;
-                            const double coef = c < W ? lrow[c] : 0.0;
-                            const double cv = c < W ? cost[c] : 0.0;
-                            ok[k] = c < W && ((has_unres && is_unres(T, vcol[c])) || coef < -prec);
-                            quo[k] = -cv / coef;
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (ok[k] && e.v < quo[k]) { e.v = quo[k]; e.i = c0 + lane + 32 * k; }
-                    }
-                    e = warp_reduce_vi<false>(e);
-                    if (e.i == INT_MAX) { status = ST_INFEASIBLE; go = 0; }  // simplex.ts:73-76
-                    else cstar = e.i;
-                }
+                if (b.i == INT_MAX) phase = 2;  // feasible (simplex.ts:51-54)
+                else rstar = b.i;
             }
-            int cnt = 0;
             if (go && rstar < 0) {  // phase 2
                 if (next_c < 0) next_c = warp_price(T, cost, vcol, W, lane, &next_neg);
                 if (next_c == 0) { status = ST_OPTIMAL; go = 0; }  // simplex.ts:265-269
-                else {
-                    cstar = next_c; isneg = next_neg;
-                    // ratio test (simplex.ts:271-296)
-                    VI m = {INFINITY, INT_MAX};
-                    int dmin = INT_MAX;
-                    for (int r0 = 0; r0 < Hn; r0 += 128) {
-                        double col[4], rv[4], quo[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int r = r0 + lane + 32 * k;
-                            const double *row = Ms + (size_t)slot[r < Hn ? r : 0] * Ws;
-                            col[k] = row[cstar]; rv[k] = row[0];
-                            quo[k] = isneg ? -rv[k] / col[k] : rv[k] / col[k];
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int r = r0 + lane + 32 * k;
-                            if (r >= Hn) continue;
-                            if (nz16(col[k])) cnt++;
-                            if (r == 0) continue;
-                            if (-prec < col[k] && col[k] < prec) continue;
-                            if (col[k] > 0 && prec > rv[k] && rv[k] > -prec) { dmin = min(dmin, r); continue; }
-                            if (quo[k] > prec && m.v > quo[k]) { m.v = quo[k]; m.i = r; }
-                        }
-                    }
-                    dmin = __reduce_min_sync(0xffffffffu, dmin);
-                    cnt = __reduce_add_sync(0xffffffffu, cnt);
-                    if (dmin != INT_MAX) rstar = dmin;
-                    else {
-                        m = warp_reduce_vi<true>(m);
-                        if (m.i != INT_MAX) rstar = m.i;
-                        else { status = ST_UNBOUNDED; unb = vcol[cstar]; go = 0; }  // simplex.ts:298-303
-                    }
+                else { cstar = next_c; isneg = next_neg; }
+            }
+            if (lane == 0) {
+                sc.mode = !go ? 0 : (rstar >= 0 ? 1 : 2);
+                sc.r = rstar; sc.c = cstar; sc.neg = isneg;
+                if (!go) {
+                    s_fin[0] = status; s_fin[1] = p1; s_fin[2] = p2; s_fin[3] = log_n; s_fin[4] = overflow; s_fin[5] = unb;
+                    s_eval = cost[0];
                 }
-            } else if (go) {  // phase-1 pivot: count the non-zero pivot-column entries
-                for (int r = lane; r < Hn; r += 32)
-                    if (nz16(Ms[(size_t)slot[r] * Ws + cstar])) cnt++;
+            }
+        }
+        NODE_CY(0);
+        __syncthreads();
+        const int mode = sc.mode;
+        if (mode == 0) break;
+        // ---- S2 (CTA): the scan that divides, one element per thread --------------------------------
+        if (mode == 1) {  // entering column of a phase-1 pivot (simplex.ts:56-76)
+            const double *cost = Ms + (size_t)slot[0] * Ws;
+            const double *lrow = Ms + (size_t)slot[sc.r] * Ws;
+            VI e = {-INFINITY, INT_MAX};
+            for (int c = 1 + tid; c < W; c += NT) {
+                const double coef = lrow[c];
+                if ((has_unres && is_unres(T, vcol[c])) || coef < -prec) {
+                    const double quo = -cost[c] / coef;
+                    if (e.v < quo) { e.v = quo; e.i = c; }
+                }
+            }
+            e = warp_reduce_vi<false>(e);
+            if (lane == 0) { part.v[warp] = e.v; part.i[warp] = e.i; }
+        } else {          // ratio test (simplex.ts:271-296)
+            const int cs = sc.c, neg = sc.neg;
+            VI m = {INFINITY, INT_MAX};
+            int dmin = INT_MAX, cnt = 0;
+            for (int r = tid; r < Hn; r += NT) {
+                const double *row = Ms + (size_t)slot[r] * Ws;
+                const double col = row[cs], rv = row[0];
+                if (nz16(col)) cnt++;
+                if (r == 0) continue;
+                if (-prec < col && col < prec) continue;
+                if (col > 0 && prec > rv && rv > -prec) { dmin = min(dmin, r); continue; }
+                const double quo = neg ? -rv / col : rv / col;
+                if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+            }
+            dmin = __reduce_min_sync(0xffffffffu, dmin);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            m = warp_reduce_vi<true>(m);
+            if (lane == 0) { part.v[warp] = m.v; part.i[warp] = m.i; part.d[warp] = dmin; part.n[warp] = cnt; }
+        }
+        NODE_CY(1);
+        __syncthreads();
+        // ---- S3 (warp 0): combine the partials, stage the pivot ------------------------------------
+        if (warp == 0) {
+            int go = 1, cnt = 0;
+            if (mode == 1) {
+                VI e = {-INFINITY, INT_MAX};
+                if (lane < NW) { e.v = part.v[lane]; e.i = part.i[lane]; }
+                e = warp_reduce_vi<false>(e);
+                if (e.i == INT_MAX) { status = ST_INFEASIBLE; go = 0; }  // simplex.ts:73-76
+                else {
+                    cstar = e.i;
+                    for (int r = lane; r < Hn; r += 32)  // non-zero pivot-column entries (lazy-flush flag)
+                        if (nz16(Ms[(size_t)slot[r] * Ws + cstar])) cnt++;
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                }
+            } else {
+                VI m = {INFINITY, INT_MAX};
+                int dmin = INT_MAX;
+                if (lane < NW) { m.v = part.v[lane]; m.i = part.i[lane]; dmin = part.d[lane]; cnt = part.n[lane]; }
+                dmin = __reduce_min_sync(0xffffffffu, dmin);
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (dmin != INT_MAX) rstar = dmin;
+                else {
+                    m = warp_reduce_vi<true>(m);
+                    if (m.i != INT_MAX) rstar = m.i;
+                    else { status = ST_UNBOUNDED; unb = vcol[cstar]; go = 0; }  // simplex.ts:298-303
+                }
             }
             if (go) {
                 const double q = Ms[(size_t)slot[rstar] * Ws + cstar];
@@ -332,39 +358,41 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
             } else if (lane == 0) {
                 piv.go = 0;
                 s_fin[0] = status; s_fin[1] = p1; s_fin[2] = p2; s_fin[3] = log_n; s_fin[4] = overflow; s_fin[5] = unb;
-                s_eval = cost[0];
+                s_eval = Ms[(size_t)slot[0] * Ws];
             }
         }
+        NODE_CY(2);
         __syncthreads();
         if (!piv.go) break;
-        const int rstar = piv.r, cstar = piv.c, flush = piv.flush, spare = s_spare;
+        const int prs = piv.r, pcs = piv.c, flush = piv.flush, spare = s_spare;
         const double q = piv.q;
-        // Both division passes at once: the lower half of the CTA normalises the pivot row
+        // ---- D (CTA): both division passes at once: the lower half of the CTA normalises the pivot row
         // (simplex.ts:352-364 + lazy flush 380-382), the upper half rewrites the pivot column
         // (simplex.ts:372-374,386-388) after staging its old entries for the row updates.
         if (tid < NT / 2) {
-            const double *praw = Ms + (size_t)slot[rstar] * Ws;
+            const double *praw = Ms + (size_t)slot[prs] * Ws;
             for (int c = tid; c < W; c += NT / 2) {
                 const double v = praw[c];
                 double f = nz16(v) ? v / q : 0.0;
-                if (c == cstar) f = 1.0 / q;
+                if (c == pcs) f = 1.0 / q;
                 if (flush && !nz16(f) && f != 0.0) f = 0.0;
                 frow[c] = f;
             }
         } else {
             for (int r = tid - NT / 2; r < Hn; r += NT / 2) {
-                if (r == rstar) { pcol[r] = 0.0; continue; }
-                double *e = Ms + (size_t)slot[r] * Ws + cstar;
+                if (r == prs) { pcol[r] = 0.0; continue; }
+                double *e = Ms + (size_t)slot[r] * Ws + pcs;
                 const double coef = *e;
                 pcol[r] = coef;
                 if (nz16(coef)) *e = -coef / q;
                 else if (coef != 0.0) *e = 0.0;
             }
         }
+        NODE_CY(3);
         __syncthreads();
-        // simplex.ts:367-391: warp 0 owns the cost row and then prices it (look-ahead, off the other
-        // warps' critical path); rows 1.. are dealt over the other warps.  A lane's columns are the
-        // same for every row, so its share of the normalised pivot row lives in registers.
+        // ---- U (CTA): simplex.ts:367-391.  Warp 0 owns the cost row and then prices it (look-ahead, off
+        // the other warps' critical path); rows 1.. are dealt over the other warps.  A lane's columns are
+        // the same for every row, so its share of the normalised pivot row lives in registers.
         for (int cb = 0; cb < W; cb += 128) {
             double fr[4];
 #pragma unroll
@@ -374,7 +402,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
             }
             const int rfirst = warp == 0 ? 0 : warp, rstep = warp == 0 ? Hn : NW - 1;
             for (int r = rfirst; r < Hn; r += rstep) {
-                if (r == rstar) {
+                if (r == prs) {
                     double *dst = Ms + (size_t)spare * Ws;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -395,7 +423,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int c = cb + lane + 32 * k;
-                    if (c < W && c != cstar && nz16(fr[k])) row[c] = __dsub_rn(v[k], __dmul_rn(coef, fr[k]));
+                    if (c < W && c != pcs && nz16(fr[k])) row[c] = __dsub_rn(v[k], __dmul_rn(coef, fr[k]));
                 }
             }
         }
@@ -403,10 +431,12 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
             __syncwarp();
             next_c = warp_price(T, Ms + (size_t)slot[0] * Ws, vcol, W, lane, &next_neg);
         }
+        NODE_CY(4);
         __syncthreads();
+        NODE_CY(5);
         if (tid == 0) {
-            const int old = slot[rstar];
-            slot[rstar] = spare;
+            const int old = slot[prs];
+            slot[prs] = spare;
             s_spare = old;
         }
         __syncwarp();  // warp 0 reads the slot table next; every other warp waits at the next barrier
@@ -443,6 +473,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, N
         r.eval_raw = s_eval; r.branch_value = mip.value;
         r.t_ns = globaltimer_ns() - t_start; r.pad = 0;
         r.tl[0] = tl0; r.tl[1] = tl1; r.tl[2] = tl2; r.tl[3] = tl3; r.tl[4] = tl4; r.tl[5] = 0;
+        for (int k = 0; k < 6; k++) r.cy[k] = cy[k];
         out->r = r;
     }
 }
