@@ -95,26 +95,21 @@ __device__ __forceinline__ VI warp_reduce_vi(VI x) {
 
 // Phase-2 pricing of the cost row (simplex.ts:140-219 without optional objectives): first batch with
 // an improving column, arg-max inside it, lowest column on ties.  Returns the column (0 = none).
-__device__ __forceinline__ int warp_price(const TabDev &T, const double *cost, const int *vcol, int W, int lane, int *neg_out) {
+// One copy each of the bulky helpers: the pivot loop has to stay inside the instruction cache (an
+// earlier fully-inlined build had a 64 KB loop body and spent most of its time fetching instructions).
+__device__ __noinline__ double node_div(double a, double b) { return a / b; }
+
+__device__ __noinline__ int warp_price(const TabDev &T, const double *cost, const int *vcol, int W, int lane, int *neg_out) {
     const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
     const bool has_unres = T.unres != nullptr;
     PriceAcc acc;
     price_init(acc, T.prec);
-    for (int c0 = 1; c0 < W; c0 += 128) {
-        double nc[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = c0 + lane + 32 * k;
-            nc[k] = c < W ? cost[c] : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = c0 + lane + 32 * k;
-            if (c >= W) continue;
-            int label = -1;
-            if (has_unres && nc[k] < 0) label = vcol[c];
-            price_consider(T, acc, c, nc[k], label, bsz);
-        }
+#pragma unroll 1
+    for (int c = 1 + lane; c < W; c += 32) {
+        const double nc = cost[c];
+        int label = -1;
+        if (has_unres && nc < 0) label = vcol[c];
+        price_consider(T, acc, c, nc, label, bsz);
     }
     // lexicographic (batch asc, value desc, column asc)
     const int mb = __reduce_min_sync(0xffffffffu, acc.myb);
@@ -245,18 +240,10 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
             if (p1 + p2 >= nb.max_pivots || log_n >= nb.log_cap) { overflow = 1; go = 0; }
             if (go && phase == 1) {
                 VI b = {-prec, INT_MAX};
-                for (int r0 = 1; r0 < Hn; r0 += 128) {
-                    double v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int r = r0 + lane + 32 * k;
-                        v[k] = r < Hn ? Ms[(size_t)slot[r] * Ws] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int r = r0 + lane + 32 * k;
-                        if (r < Hn && v[k] < b.v) { b.v = v[k]; b.i = r; }
-                    }
+#pragma unroll 2
+                for (int r = 1 + lane; r < Hn; r += 32) {
+                    const double v = Ms[(size_t)slot[r] * Ws];
+                    if (v < b.v) { b.v = v; b.i = r; }
                 }
                 b = warp_reduce_vi<true>(b);
                 if (b.i == INT_MAX) phase = 2;  // feasible (simplex.ts:51-54)
@@ -285,10 +272,11 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
             const double *cost = Ms + (size_t)slot[0] * Ws;
             const double *lrow = Ms + (size_t)slot[sc.r] * Ws;
             VI e = {-INFINITY, INT_MAX};
+#pragma unroll 1
             for (int c = 1 + tid; c < W; c += NT) {
                 const double coef = lrow[c];
                 if ((has_unres && is_unres(T, vcol[c])) || coef < -prec) {
-                    const double quo = -cost[c] / coef;
+                    const double quo = node_div(-cost[c], coef);
                     if (e.v < quo) { e.v = quo; e.i = c; }
                 }
             }
@@ -298,6 +286,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
             const int cs = sc.c, neg = sc.neg;
             VI m = {INFINITY, INT_MAX};
             int dmin = INT_MAX, cnt = 0;
+#pragma unroll 1
             for (int r = tid; r < Hn; r += NT) {
                 const double *row = Ms + (size_t)slot[r] * Ws;
                 const double col = row[cs], rv = row[0];
@@ -305,7 +294,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
                 if (r == 0) continue;
                 if (-prec < col && col < prec) continue;
                 if (col > 0 && prec > rv && rv > -prec) { dmin = min(dmin, r); continue; }
-                const double quo = neg ? -rv / col : rv / col;
+                const double quo = node_div(neg ? -rv : rv, col);  // (-rhs) / col == -rhs / col
                 if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
             }
             dmin = __reduce_min_sync(0xffffffffu, dmin);
@@ -325,6 +314,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
                 if (e.i == INT_MAX) { status = ST_INFEASIBLE; go = 0; }  // simplex.ts:73-76
                 else {
                     cstar = e.i;
+#pragma unroll 1
                     for (int r = lane; r < Hn; r += 32)  // non-zero pivot-column entries (lazy-flush flag)
                         if (nz16(Ms[(size_t)slot[r] * Ws + cstar])) cnt++;
                     cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -371,20 +361,22 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
         // (simplex.ts:372-374,386-388) after staging its old entries for the row updates.
         if (tid < NT / 2) {
             const double *praw = Ms + (size_t)slot[prs] * Ws;
+#pragma unroll 1
             for (int c = tid; c < W; c += NT / 2) {
                 const double v = praw[c];
-                double f = nz16(v) ? v / q : 0.0;
-                if (c == pcs) f = 1.0 / q;
+                double f = node_div(c == pcs ? 1.0 : v, q);
+                if (c != pcs && !nz16(v)) f = 0.0;
                 if (flush && !nz16(f) && f != 0.0) f = 0.0;
                 frow[c] = f;
             }
         } else {
+#pragma unroll 1
             for (int r = tid - NT / 2; r < Hn; r += NT / 2) {
                 if (r == prs) { pcol[r] = 0.0; continue; }
                 double *e = Ms + (size_t)slot[r] * Ws + pcs;
                 const double coef = *e;
                 pcol[r] = coef;
-                if (nz16(coef)) *e = -coef / q;
+                if (nz16(coef)) *e = node_div(-coef, q);
                 else if (coef != 0.0) *e = 0.0;
             }
         }
@@ -393,6 +385,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
         // ---- U (CTA): simplex.ts:367-391.  Warp 0 owns the cost row and then prices it (look-ahead, off
         // the other warps' critical path); rows 1.. are dealt over the other warps.  A lane's columns are
         // the same for every row, so its share of the normalised pivot row lives in registers.
+#pragma unroll 1
         for (int cb = 0; cb < W; cb += 128) {
             double fr[4];
 #pragma unroll
@@ -401,6 +394,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
                 fr[k] = c < W ? frow[c] : 0.0;
             }
             const int rfirst = warp == 0 ? 0 : warp, rstep = warp == 0 ? Hn : NW - 1;
+#pragma unroll 1
             for (int r = rfirst; r < Hn; r += rstep) {
                 if (r == prs) {
                     double *dst = Ms + (size_t)spare * Ws;
