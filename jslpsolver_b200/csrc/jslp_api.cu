@@ -140,9 +140,10 @@ struct jslp_tab {
     int64_t host_log_cap = 0;
     std::vector<int4> host_log;
     // graphs
-    cudaGraphExec_t g_fused = nullptr, g_simple = nullptr;
+    // [0 = fused, 1 = two-kernel][kind]: kinds 0..N_KINDS-2 are the geometrically growing first
+    // batches of a solve (24, 48, 96, 192 steps), the last kind is the steady-state batch; built lazily
+    cudaGraphExec_t graphs[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
     int g_batch = 0, g_grid = 0, g_smem = 0;
-    cudaGraphExec_t g_fused_small = nullptr, g_simple_small = nullptr;  // first batch of every solve
     cudaEvent_t ev_slot[2] = {nullptr, nullptr};
     Saved saved;
     Snapshot snaps[2];  // one restart point per in-flight batch
@@ -197,12 +198,13 @@ extern "C" int jslp_ctx_sync(jslp_ctx *c) {
     return JSLP_OK;
 }
 
+static const int N_KINDS = 5;
 static void drop_graphs(jslp_tab *t) {
-    if (t->g_fused) cudaGraphExecDestroy(t->g_fused);
-    if (t->g_simple) cudaGraphExecDestroy(t->g_simple);
-    if (t->g_fused_small) cudaGraphExecDestroy(t->g_fused_small);
-    if (t->g_simple_small) cudaGraphExecDestroy(t->g_simple_small);
-    t->g_fused = t->g_simple = t->g_fused_small = t->g_simple_small = nullptr;
+    for (int e = 0; e < 2; e++)
+        for (int k = 0; k < N_KINDS; k++) {
+            if (t->graphs[e][k]) cudaGraphExecDestroy(t->graphs[e][k]);
+            t->graphs[e][k] = nullptr;
+        }
 }
 
 static int push_desc(jslp_tab *t) {
@@ -476,67 +478,80 @@ static int ensure_step_bufs(jslp_tab *t, int grid) {
     return push_desc(t);
 }
 
+// Steps in a batch of kind k.  A solve starts with short batches that double (most node LPs of a
+// branch-and-cut end inside them, and every step enqueued past the end of a solve is a wasted launch)
+// and settles on the configured batch length.
+static int batch_steps(const jslp_tab *t, int kind) {
+    return kind >= N_KINDS - 1 ? t->batch : std::min(SMALL_BATCH << kind, std::max(1, t->batch));
+}
+
+// Validates the graph cache against the current launch geometry (drops it when stale).
 static int build_graphs(jslp_tab *t) {
     const int grid = step_grid(t);
     const int smem = t->stride * 8;
     int rc = ensure_step_bufs(t, grid);
     if (rc) return rc;
-    if (t->g_fused && t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem &&
-        t->g_variant == t->variant + 100 * (t->pdl == 1) + 1000 * t->pingpong)
-        return JSLP_OK;
+    const int key = t->variant + 100 * (t->pdl == 1) + 1000 * t->pingpong;
+    if (t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem && t->g_variant == key) return JSLP_OK;
     drop_graphs(t);
+    CK(cudaFuncSetAttribute(step_variant(t).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = key;
+    return JSLP_OK;
+}
+
+// The graph of `kind` for engine index eidx (0 = fused, 1 = two kernels per pivot); captured on first use.
+static int get_graph(jslp_tab *t, int eidx, int kind, cudaGraphExec_t *out) {
+    if (t->graphs[eidx][kind]) { *out = t->graphs[eidx][kind]; return JSLP_OK; }
+    const int grid = step_grid(t);
+    const int smem = t->stride * 8;
     cudaStream_t s = t->ctx->stream;
     const StepVariant &sv = step_variant(t);
-    CK(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // 2 = ping-pong step: the last two CTAs of the grid are the selectors (at least one row CTA besides them)
     const int fused_mode = (t->pingpong && t->lookahead && grid >= 3) ? 2 : 1;
-    for (int mode = 0; mode < 4; mode++) {  // {fused, two-kernel} x {long batch, short first batch}
-        const int nsteps = mode >= 2 ? SMALL_BATCH : t->batch;
-        cudaGraph_t g;
-        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
-        if ((mode & 1) == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
-            k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-            for (int i = 0; i < nsteps; i++) {
-                if (t->pdl == 1 && i > 0) {
-                    // programmatic dependent launch: step i's CTAs are scheduled while step i-1
-                    // drains and block in griddepcontrol.wait until it has completed
-                    cudaLaunchConfig_t cfg;
-                    memset(&cfg, 0, sizeof(cfg));
-                    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sv.threads);
-                    cfg.dynamicSmemBytes = smem; cfg.stream = s;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    at[0].val.programmaticStreamSerializationAllowed = 1;
-                    cfg.attrs = at; cfg.numAttrs = 1;
-                    TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = fused_mode; const double *a3 = t->hd.prow; int a4 = t->stride;
-                    void *args[] = {&a0, &a1, &a2, &a3, &a4};
-                    cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args);
-                    if (le != cudaSuccess) {
-                        cudaGraph_t junk;
-                        cudaStreamEndCapture(s, &junk);
-                        return fail(JSLP_E_CUDA, std::string("PDL launch: ") + cudaGetErrorString(le));
-                    }
-                } else {
-                    sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, fused_mode, t->hd.prow, t->stride);
+    const int nsteps = batch_steps(t, kind);
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
+    if (eidx == 0) {  // fused: one launch per pivot, last CTA selects the next pivot
+        k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
+        for (int i = 0; i < nsteps; i++) {
+            if (t->pdl == 1 && i > 0) {
+                // programmatic dependent launch: step i's CTAs are scheduled while step i-1
+                // drains and block in griddepcontrol.wait until it has completed
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sv.threads);
+                cfg.dynamicSmemBytes = smem; cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = fused_mode; const double *a3 = t->hd.prow; int a4 = t->stride;
+                void *args[] = {&a0, &a1, &a2, &a3, &a4};
+                cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args);
+                if (le != cudaSuccess) {
+                    cudaGraph_t junk;
+                    cudaStreamEndCapture(s, &junk);
+                    return fail(JSLP_E_CUDA, std::string("PDL launch: ") + cudaGetErrorString(le));
                 }
-            }
-        } else {  // two kernels per pivot
-            for (int i = 0; i < nsteps; i++) {
-                k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-                sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0, t->hd.prow, t->stride);
+            } else {
+                sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, fused_mode, t->hd.prow, t->stride);
             }
         }
-        cudaError_t e = cudaStreamEndCapture(s, &g);
-        if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-        cudaGraphExec_t ge;
-        e = cudaGraphInstantiate(&ge, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-        if (mode == 0) t->g_fused = ge; else if (mode == 1) t->g_simple = ge;
-        else if (mode == 2) t->g_fused_small = ge; else t->g_simple_small = ge;
+    } else {  // two kernels per pivot
+        for (int i = 0; i < nsteps; i++) {
+            k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
+            sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, 0, t->hd.prow, t->stride);
+        }
     }
-    t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = t->variant + 100 * (t->pdl == 1) + 1000 * t->pingpong;
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t ge;
+    e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    t->graphs[eidx][kind] = ge;
+    *out = ge;
     return JSLP_OK;
 }
 
@@ -745,11 +760,8 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     rc = build_graphs(t);
     if (rc) return rc;
     const int engine = (t->engine == 1) ? 1 : 2;
-    // the first batch of a solve is short (most node LPs end inside it); later ones are long
-    cudaGraphExec_t graphs[2] = {engine == 1 ? t->g_simple_small : t->g_fused_small,
-                                 engine == 1 ? t->g_simple : t->g_fused};
-    const int sizes[2] = {SMALL_BATCH, t->batch};
-    auto launches_of = [&](int k) { return engine == 1 ? 1 + 2 * (int64_t)sizes[k] : 2 + (int64_t)sizes[k]; };
+    const int eidx = engine == 1 ? 1 : 0;
+    auto launches_of = [&](int k) { return engine == 1 ? 1 + 2 * (int64_t)batch_steps(t, k) : 2 + (int64_t)batch_steps(t, k); };
     const int64_t launches0 = ctx->launches;
     const int cap = t->hd.plog_cap;
 
@@ -796,7 +808,7 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             const int fused_mode = (t->pingpong && t->lookahead && grid >= 3) ? 2 : 1;
             k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
             k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-            for (int i = 0; i < sizes[kind]; i++) {
+            for (int i = 0; i < batch_steps(t, kind); i++) {
                 cudaLaunchConfig_t cfg;
                 memset(&cfg, 0, sizeof(cfg));
                 cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sv.threads);
@@ -810,7 +822,10 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
                 CK(cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args));
             }
         } else {
-            CK(cudaGraphLaunch(graphs[kind], s));
+            cudaGraphExec_t ge;
+            int e = get_graph(t, eidx, kind, &ge);
+            if (e) return e;
+            CK(cudaGraphLaunch(ge, s));
         }
         ctx->launches += launches_of(kind);
         CK(cudaMemcpyAsync(t->h_rec + slot, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
@@ -823,9 +838,11 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     if (rc) return rc;
     for (int i = 0;; i++) {
         const int slot = i & 1;
-        const bool ahead = i >= 1;  // speculate only once a solve has outlived its first batch
+        // enqueue the next batch ahead of the wait only once the solve has reached the steady-state
+        // batch length; while the batches are still growing the next one is enqueued after the wait
+        const bool ahead = i >= N_KINDS - 1;
         if (ahead) {
-            rc = enqueue(slot ^ 1, 1);
+            rc = enqueue(slot ^ 1, N_KINDS - 1);
             if (rc) return rc;
         }
         CK(cudaEventSynchronize(t->ev_slot[slot]));
@@ -861,7 +878,10 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             if (t->hd.part) CK(cudaMemsetAsync(t->hd.part, 0xff, sizeof(Part) * (size_t)t->part_cap, s));
             CK(cudaMemcpyAsync(t->d_rec, t->h_rec + slot, sizeof(Rec), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
-            CK(cudaGraphLaunch(graphs[kind_of[slot]], s));
+            cudaGraphExec_t ge;
+            rc = get_graph(t, eidx, kind_of[slot], &ge);
+            if (rc) return rc;
+            CK(cudaGraphLaunch(ge, s));
             ctx->launches += launches_of(kind_of[slot]);
             CK(cudaMemcpyAsync(t->h_rec + slot, t->d_rec, sizeof(Rec), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
@@ -880,7 +900,7 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             break;
         }
         if (!ahead) {
-            rc = enqueue(slot ^ 1, 1);
+            rc = enqueue(slot ^ 1, std::min(i + 1, N_KINDS - 1));
             if (rc) return rc;
         }
     }

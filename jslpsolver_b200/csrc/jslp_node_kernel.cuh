@@ -97,7 +97,14 @@ __device__ __forceinline__ VI warp_reduce_vi(VI x) {
 // an improving column, arg-max inside it, lowest column on ties.  Returns the column (0 = none).
 // One copy each of the bulky helpers: the pivot loop has to stay inside the instruction cache (an
 // earlier fully-inlined build had a 64 KB loop body and spent most of its time fetching instructions).
-__device__ __noinline__ double node_div(double a, double b) { return a / b; }
+// IEEE division.  A zero dividend sends the compiler's division to its slow path (~420 cycles
+// instead of ~125 on B200) and degenerate tableaux are full of zeros, so that case is answered
+// directly: 0 / b = 0 with the sign of a xor b for every b that is neither 0 nor NaN.
+__device__ __noinline__ double node_div(double a, double b) {
+    if (a == 0.0 && b == b && b != 0.0)
+        return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull);
+    return a / b;
+}
 
 __device__ __noinline__ int warp_price(const TabDev &T, const double *cost, const int *vcol, int W, int lane, int *neg_out) {
     const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
@@ -364,8 +371,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
 #pragma unroll 1
             for (int c = tid; c < W; c += NT / 2) {
                 const double v = praw[c];
-                double f = node_div(c == pcs ? 1.0 : v, q);
-                if (c != pcs && !nz16(v)) f = 0.0;
+                double f = (c == pcs || nz16(v)) ? node_div(c == pcs ? 1.0 : v, q) : 0.0;
                 if (flush && !nz16(f) && f != 0.0) f = 0.0;
                 frow[c] = f;
             }

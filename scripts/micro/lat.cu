@@ -53,18 +53,36 @@ __global__ void k(double a, double b, int n, long long *out, double *sink) {
     t0 = clock64();
     for (int i = 0; i < n; i++) x = __dsub_rn(x, __dmul_rn(y, x));
     t1 = clock64(); if (lane == 0) out[9] = (t1 - t0);
-    sink[threadIdx.x] = x + u + idx;
+    // zero dividend: does 0/y leave the division fast path?
+    t0 = clock64();
+    for (int i = 0; i < n; i++) x = (x - x) / y + a;
+    t1 = clock64(); if (lane == 0) out[10] = (t1 - t0);
+    // half the lanes divide zero
+    t0 = clock64();
+    for (int i = 0; i < n; i++) x = ((lane & 1) ? x : 0.0) / y + a;
+    t1 = clock64(); if (lane == 0) out[11] = (t1 - t0);
+    // tiny quotient (1e-300 scale)
+    double w = 1e-300 * (1 + lane);
+    t0 = clock64();
+    for (int i = 0; i < n; i++) w = w / y;
+    t1 = clock64(); if (lane == 0) out[12] = (t1 - t0);
+    // huge divisor / small dividend mix, typical tableau magnitudes
+    w = 3.5 + lane;
+    t0 = clock64();
+    for (int i = 0; i < n; i++) w = 1.0 / (w + 1e-3);
+    t1 = clock64(); if (lane == 0) out[13] = (t1 - t0);
+    sink[threadIdx.x] = x + u + idx + w;
 }
 int main() {
     long long *out; double *sink;
-    cudaMallocManaged(&out, 80); cudaMalloc(&sink, 8 * 256);
+    cudaMallocManaged(&out, 160); cudaMalloc(&sink, 8 * 256);
     const int n = 256;
-    const char *names[] = {"DFMA", "DADD", "DDIV+DADD", "4xDDIV+DADD (per iter)", "REDUX(+IADD)", "SHFL(+IADD)", "DSETP+SEL+DADD", "LDS chase", "BAR.SYNC", "DMUL+DSUB"};
+    const char *names[] = {"DFMA", "DADD", "DDIV+DADD", "4xDDIV+DADD (per iter)", "REDUX(+IADD)", "SHFL(+IADD)", "DSETP+SEL+DADD", "LDS chase", "BAR.SYNC", "DMUL+DSUB", "0/y + DADD", "half lanes 0/y + DADD", "1e-300/y", "1/(w+eps)"};
     for (int threads : {32, 256}) {
         k<<<1, threads>>>(1.000001, 0.999999, n, out, sink); cudaDeviceSynchronize();
         k<<<1, threads>>>(1.000001, 0.999999, n, out, sink); cudaDeviceSynchronize();
         printf("threads %d\n", threads);
-        for (int i = 0; i < 10; i++) printf("  %-26s %.1f cycles\n", names[i], (double)out[i] / n);
+        for (int i = 0; i < 14; i++) printf("  %-26s %.1f cycles\n", names[i], (double)out[i] / n);
     }
     return 0;
 }
