@@ -538,6 +538,229 @@ __device__ void cta_selector_decide(TabDev *Tp, const TabDev &T, Rec *rec, SelSm
     }
 }
 
+// Waits for the message tagged `seq` in `slot` (handshakes between the two selector CTAs).
+__device__ __forceinline__ void part_wait(const Part *slot, unsigned int seq) {
+    double dq;
+    int d1, d2, d3;
+    const long long tstart = clock64();
+    while (!part_try_read(slot, seq, &dq, &d1, &d2, &d3)) {
+        __nanosleep(20);
+        if (clock64() - tstart > 4000000000LL) break;
+    }
+}
+
+// Selector of a ping-pong step that executes a PHASE-1 pivot (rstar, cstar, q).  The row CTAs publish,
+// before they stream, the most negative right-hand side their rows will have after this pivot; this
+// CTA reduces those to the next leaving row (simplex.ts:38-54), derives that row and the cost row as
+// this pivot leaves them from the OLD tableau (new_entry), picks the entering column (56-76), counts
+// the non-zero entries of the next pivot column (lazy-flush flag), stages the next pivot row already
+// normalised and flips the descriptor -- all while the row CTAs stream.  When no infeasible row is
+// left it opens phase 2 itself (pricing 129-269, ratio test 271-296), again from derived values.
+__device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
+                                       int rstar, int cstar, double q, int launch, int p1, int log_n, bool stop_after,
+                                       int only_phase) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const double *src = T.M;
+    const size_t stride = (size_t)T.stride;
+    const int W = T.W, H = T.H;
+    const double prec = T.prec;
+    const double coef0 = ldg_cg(src + cstar);  // cost-row entry of the executing pivot's column
+    const unsigned int seq = (unsigned int)(launch + 1);
+    auto flip = [&]() {  // the updated tableau becomes the current one
+        Tp->M = T.M2;
+        Tp->M2 = T.M;
+    };
+    auto finish = [&](int status, int phase, int unb) {  // no further pivot: final record (tid 0 only)
+        rec->done = launch + 1; rec->p1 = p1 + 1; rec->has_pivot = 0;
+        if (status != ST_RUNNING) {
+            rec->status = status;
+            if (phase) rec->phase = phase;
+            if (unb >= 0) rec->unbounded_var = unb;
+            rec->eval_raw = new_entry(ldg_cg(src), false, coef0, frow[0], false, q);
+        }
+        flip();
+    };
+    if (stop_after) {  // replay stop: execute this pivot and select nothing
+        if (tid == 0) finish(ST_RUNNING, 0, -1);
+        return;
+    }
+    int rnext, cnt_unused;
+    if (!cta_collect_partials(T, s, G, seq, &rnext, &cnt_unused)) {
+        if (tid == 0) { rec->status = ST_ERROR; rec->has_pivot = 0; }
+        return;
+    }
+    int phase_next = 1, cn = 0, isneg = 0, cnt = 0;
+    const bool has_unres = T.unres != nullptr;
+    if (rnext >= 0) {
+        // ---- phase 1 goes on: entering column of row rnext (simplex.ts:56-76) on derived entries
+        const double *rowp = src + (size_t)rnext * stride;
+        const bool is_prow = rnext == rstar;
+        const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
+        const VI einit = {-INFINITY, INT_MAX};
+        VI e = einit;
+        for (int c0 = 1; c0 < W; c0 += 8 * NT) {
+            double rv[8], cv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = c0 + tid + k * NT;
+                rv[k] = c < W ? ldg_cg(rowp + c) : 0.0;
+                cv[k] = c < W ? ldg_cg(src + c) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = c0 + tid + k * NT;
+                if (c >= W) continue;
+                const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
+                if ((has_unres && is_unres(T, T.vcol[c])) || ur < -prec) {
+                    const double uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
+                    const double quo = -uc / ur;
+                    if (e.v < quo) { e.v = quo; e.i = c; }
+                }
+            }
+        }
+        e = block_reduce_vi<false>(e, einit, s.red);
+        if (e.i == INT_MAX) {  // simplex.ts:73-76
+            if (tid == 0) finish(ST_INFEASIBLE, 0, -1);
+            return;
+        }
+        cn = e.i;
+        // non-zero entries of the next pivot column as this pivot leaves it (all rows, incl. row 0)
+        const double f_cn = frow[cn];
+        for (int rb = 0; rb < H; rb += 8 * NT) {
+            double a[8], cf[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rb + tid + k * NT;
+                a[k] = r < H ? ldg_cg(src + (size_t)r * stride + cn) : 0.0;
+                cf[k] = (r < H && r != rstar) ? ldg_cg(src + (size_t)r * stride + cstar) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rb + tid + k * NT;
+                if (r < H && nz16(new_entry(a[k], r == rstar, cf[k], f_cn, cn == cstar, q))) cnt++;
+            }
+        }
+        cnt = block_reduce_int<1>(cnt, s.red);
+    } else {
+        // ---- feasible after this pivot (simplex.ts:51-54)
+        if (only_phase == 1) {
+            if (tid == 0) finish(ST_P1_DONE, 0, -1);
+            return;
+        }
+        phase_next = 2;
+        // pricing (simplex.ts:140-219) of the cost row as this pivot leaves it
+        {
+            const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
+            PriceAcc acc;
+            price_init(acc, prec);
+            for (int c0 = 1; c0 < W; c0 += 8 * NT) {
+                double cv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int c = c0 + tid + k * NT;
+                    cv[k] = c < W ? ldg_cg(src + c) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int c = c0 + tid + k * NT;
+                    if (c >= W) continue;
+                    const double nc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
+                    int label = -1;
+                    if (has_unres && nc < 0) label = T.vcol[c];
+                    price_consider(T, acc, c, nc, label, bsz);
+                }
+            }
+            price_finish(T, s, acc, &cn, &isneg);
+        }
+        if (cn == 0) {  // optimal (simplex.ts:265-269)
+            if (tid == 0) finish(ST_OPTIMAL, 2, -1);
+            return;
+        }
+        // ratio test (simplex.ts:271-296) on the derived pivot column and right-hand side
+        const VI init = {INFINITY, INT_MAX};
+        VI m = init;
+        int dmin = INT_MAX;
+        const double f_cn = frow[cn], f_0 = frow[0];
+        for (int rb = 0; rb < H; rb += 8 * NT) {
+            double a[8], b0[8], cf[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rb + tid + k * NT;
+                a[k] = r < H ? ldg_cg(src + (size_t)r * stride + cn) : 0.0;
+                b0[k] = r < H ? ldg_cg(src + (size_t)r * stride) : 0.0;
+                cf[k] = (r < H && r != rstar) ? ldg_cg(src + (size_t)r * stride + cstar) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rb + tid + k * NT;
+                if (r >= H) continue;
+                const double col = new_entry(a[k], r == rstar, cf[k], f_cn, cn == cstar, q);
+                const double rhs = new_entry(b0[k], r == rstar, cf[k], f_0, false, q);
+                T.pcol[r] = col;  // the step that executes this pivot runs in place and reads its column here
+                if (nz16(col)) cnt++;
+                if (r == 0) continue;
+                if (-prec < col && col < prec) continue;
+                if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
+                const double quo = isneg ? -rhs / col : rhs / col;
+                if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
+            }
+        }
+        block_reduce_ratio(dmin, m, cnt, s.red);
+        if (dmin != INT_MAX) rnext = dmin;
+        else if (m.i != INT_MAX) rnext = m.i;
+        else {  // unbounded (simplex.ts:298-303)
+            if (tid == 0) finish(ST_UNBOUNDED, 2, T.vcol[cn]);
+            return;
+        }
+    }
+    // ---- stage pivot (rnext, cn): normalised row into the prow side buffer, labels, log, record
+    const double *rowp = src + (size_t)rnext * stride;
+    const bool is_prow = rnext == rstar;
+    const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
+    const double qn = new_entry(ldg_cg(rowp + cn), is_prow, coef_r, frow[cn], cn == cstar, q);
+    const bool flushn = (cnt - (nz16(qn) ? 1 : 0)) > 0;
+    const int leaving = T.vrow[rnext];
+    const int entering = T.vcol[cn];
+    if (tid == 0) part_wait(T.part + G + 1, seq);  // the other selector's TMA read of prow has landed
+    __syncthreads();
+    for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
+        double rv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            rv[k] = c < W ? ldg_cg(rowp + c) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = c0 + tid + k * NT;
+            if (c >= T.stride) continue;
+            double f = 0.0;
+            if (c < W) {
+                const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
+                f = nz16(ur) ? ur / qn : 0.0;
+                if (c == cn) f = 1.0 / qn;
+                if (flushn && !nz16(f) && f != 0.0) f = 0.0;
+            }
+            T.prow[c] = f;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rnext | (phase_next == 2 ? (1 << 30) : 0), cn, leaving, entering);
+        rec->log_n = log_n + 1;
+        T.vrow[rnext] = entering;  // simplex.ts:339-349
+        T.vcol[cn] = leaving;
+        rec->done = launch + 1; rec->p1 = p1 + 1;
+        rec->phase = phase_next; rec->r = rnext; rec->c = cn; rec->q = qn; rec->is_neg = isneg;
+        rec->flush = flushn;
+        rec->has_pivot = 1;
+        rec->next_c = -1;    // the pivot after this one has not been priced
+        rec->prow_norm = 1;  // the row above is already normalised
+        __threadfence();     // prow and the record are read by the next launch
+        flip();
+    }
+}
+
 // Selector S2 of a ping-pong step: stages the raw pivot row of the next pivot (the row as the
 // executing pivot leaves it) into the prow side buffer, the TMA source of the next launch.
 __device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G, int rstar,
@@ -645,9 +868,11 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     // Grid = G row CTAs + 2 selector CTAs (decide, stage).  Eligible: phase 2 with the next entering
     // column already priced, no optional objectives, at most 32 rows per CTA (one warp runs the
     // look-ahead ratio test of the CTA's rows).
-    const bool pp = do_select == 2 && next_c >= 0 && phase == 2 && T.nOpt == 0 && T.M2 != nullptr && base + 1 <= 32;
+    const bool pp_ok = do_select == 2 && T.nOpt == 0 && T.M2 != nullptr && base + 1 <= 32;
+    const bool pp1 = pp_ok && phase == 1;                 // phase-1 pivot: the selector decides everything
+    const bool pp = pp1 || (pp_ok && next_c >= 0 && phase == 2);
     if (pp) {
-        const bool want_partial = next_c > 0 && !stop_after;
+        const bool want_partial = pp1 ? !stop_after : (next_c > 0 && !stop_after);
         const int lw = (NT >> 5) - 1;           // the warp that runs the look-ahead (last warp)
         const int lane = tid & 31;
         const bool la_warp = (tid >> 5) == lw && b < G;
@@ -661,13 +886,36 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                 const size_t off = (size_t)(r0 + lane) * T.stride;
                 la_coef = ldg_cg(T.M + off + cstar);
                 if (want_partial) {
-                    la_col = ldg_cg(T.M + off + next_c);
+                    if (!pp1) la_col = ldg_cg(T.M + off + next_c);
                     la_rhs = ldg_cg(T.M + off);
                 }
             }
-            if (want_partial) { raw_n = ldg_cg(prow_arg + next_c); raw_0 = ldg_cg(prow_arg); }
+            if (want_partial) { if (!pp1) raw_n = ldg_cg(prow_arg + next_c); raw_0 = ldg_cg(prow_arg); }
             if (lane < nr) s_coef[lane] = la_coef;
-            if (want_partial) {
+            if (want_partial && pp1) {
+                // phase 1: the most negative right-hand side of this CTA's rows after this pivot
+                double f_0 = raw_0;
+                if (!prow_norm) {
+                    f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
+                    if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
+                }
+                const bool is_prow = (r0 + lane) == rstar;
+                const double rhs = new_entry(la_rhs, is_prow, la_coef, f_0, false, q);
+                VI m = {INFINITY, INT_MAX};
+                if (lane < nr && r0 + lane != 0 && rhs < -T.prec) { m.v = rhs; m.i = lane; }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    VI y;
+                    y.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+                    y.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+                    if (better<true>(y, m)) m = y;
+                }
+                if (lane == 0) {
+                    mbar_wait(&bar, 0);  // a published partial also promises: this CTA is done reading prow
+                    part_publish(T.part + b, m.v, m.i == INT_MAX ? 255 : m.i, 255, 0, (unsigned int)(launch + 1));
+                    if (dbg) T.dbg[((size_t)launch * T.dbg_grid + b) * 8 + 2] = clock64() - s_t0;
+                }
+            } else if (want_partial) {
                 double f_n = raw_n, f_0 = raw_0;
                 if (!prow_norm) {
                     f_n = nz16(raw_n) ? raw_n / q : 0.0;
@@ -722,7 +970,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         }
         __syncthreads();
         if (dbg && tid == 0) t1 = clock64();
-        if (b == G) {
+        if (pp1 && b == G) {
+            cta_selector_decide_p1(Tp, T, rec, sel, frow, G, rstar, cstar, q, launch, p1, log_n0, stop_after, rec->only_phase);
+            if (dbg && tid == 0) t2 = t3 = clock64();
+        } else if (pp1 && b == G + 1) {
+            // idle in a phase-1 step; tells the deciding selector that its TMA read of prow has landed
+            if (tid == 0) part_publish(T.part + G + 1, 0.0, 255, 255, 0, (unsigned int)(launch + 1));
+            if (dbg && tid == 0) t2 = t3 = clock64();
+        } else if (b == G) {
             long long ts[3] = {0, 0, 0};
             // tell the staging selector that this CTA's TMA read of the prow buffer has landed
             if (tid == 0) part_publish(T.part + G, 0.0, 255, 255, 0, (unsigned int)(launch + 1));
