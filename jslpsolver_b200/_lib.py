@@ -96,6 +96,8 @@ def load(build_if_missing: bool = True):
         except Exception as e:  # stale-but-present library on a box without nvcc is still usable
             if not os.path.exists(path):
                 raise JslpError(f"libjslp_b200.so is missing and could not be built: {e}") from e
+    if os.environ.get("JSLP_LIB"):  # A/B builds of the same ABI (tuning aid)
+        path = os.environ["JSLP_LIB"]
     if not os.path.exists(path):
         raise JslpError("libjslp_b200.so is missing: run `python -m jslpsolver_b200.build` (no CPU fallback)")
     L = C.CDLL(path)

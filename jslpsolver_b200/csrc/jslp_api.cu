@@ -428,21 +428,19 @@ extern "C" int jslp_debug_timeline(jslp_tab *t, int64_t *out, int64_t cap_values
 // Instantiations of the fused step: <threads, min CTAs/SM, rows per pass, software prefetch>.
 typedef void (*step_fn_t)(TabDev *, Rec *, int, const double *, int);
 struct StepVariant {
-    step_fn_t fn;
+    step_fn_t fn;      // in-place step (two-kernel engine, optional objectives, more than 32 rows per CTA)
+    step_fn_t fn_pp;   // ping-pong step: grid = row CTAs + 2 selector CTAs
     int threads, ctas_per_sm;
     const char *name;
 };
+#define JSLP_VARIANT(T, O, RC, PF) k_pivot_step<T, O, RC, PF, false>, k_pivot_step<T, O, RC, PF, true>, T, O
 static const StepVariant STEP_VARIANTS[] = {
-    {k_pivot_step<256, 2, 8, false>, 256, 2, "t256 occ2 rc8"},
-    {k_pivot_step<256, 2, 4, true>, 256, 2, "t256 occ2 rc4 prefetch"},
-    {k_pivot_step<256, 4, 4, false>, 256, 4, "t256 occ4 rc4"},
-    {k_pivot_step<512, 1, 8, false>, 512, 1, "t512 occ1 rc8"},
-    {k_pivot_step<256, 3, 4, true>, 256, 3, "t256 occ3 rc4 prefetch"},
-    {k_pivot_step<128, 8, 4, false>, 128, 8, "t128 occ8 rc4"},
-    {k_pivot_step<256, 4, 2, true>, 256, 4, "t256 occ4 rc2 prefetch"},
-    {k_pivot_step<256, 2, 8, true>, 256, 2, "t256 occ2 rc8 prefetch"},
-    {k_pivot_step<384, 1, 8, true>, 384, 1, "t384 occ1 rc8 prefetch"},
-    {k_pivot_step<512, 1, 8, true>, 512, 1, "t512 occ1 rc8 prefetch"},
+    {JSLP_VARIANT(256, 2, 8, false), "t256 occ2 rc8"},
+    {JSLP_VARIANT(256, 2, 4, true), "t256 occ2 rc4 prefetch"},
+    {JSLP_VARIANT(256, 4, 4, false), "t256 occ4 rc4"},
+    {JSLP_VARIANT(512, 1, 8, false), "t512 occ1 rc8"},
+    {JSLP_VARIANT(256, 3, 4, true), "t256 occ3 rc4 prefetch"},
+    {JSLP_VARIANT(128, 8, 4, false), "t128 occ8 rc4"},
 };
 static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VARIANTS[0]));
 static const int SMALL_BATCH = 24;  // steps in the first graph of a solve
@@ -453,6 +451,14 @@ static int step_grid(const jslp_tab *t) {
     const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : step_variant(t).ctas_per_sm;
     int g = t->ctx->num_sms * per_sm;
     return std::max(1, std::min(g, t->rowcap));
+}
+
+// The ping-pong step applies to a whole solve or not at all (the graph holds one kernel): no optional
+// objectives, the second tableau buffer, and at most 32 rows per row CTA (one warp runs the look-ahead).
+static bool use_pp(const jslp_tab *t) {
+    const int grid = step_grid(t);
+    if (!(t->pingpong && t->lookahead && t->nOpt == 0 && grid >= 3 && t->hd.M2 != nullptr)) return false;
+    return t->H / (grid - 2) + 1 <= 32;
 }
 
 // (re)allocates the buffers that depend on the step grid: look-ahead partials, debug timeline
@@ -491,10 +497,11 @@ static int build_graphs(jslp_tab *t) {
     const int smem = t->stride * 8;
     int rc = ensure_step_bufs(t, grid);
     if (rc) return rc;
-    const int key = t->variant + 100 * (t->pdl == 1) + 1000 * t->pingpong;
+    const int key = t->variant + 100 * (t->pdl == 1) + 1000 * (use_pp(t) ? 1 : 0);
     if (t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem && t->g_variant == key) return JSLP_OK;
     drop_graphs(t);
     CK(cudaFuncSetAttribute(step_variant(t).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(step_variant(t).fn_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     t->g_batch = t->batch; t->g_grid = grid; t->g_smem = smem; t->g_variant = key;
     return JSLP_OK;
 }
@@ -506,8 +513,10 @@ static int get_graph(jslp_tab *t, int eidx, int kind, cudaGraphExec_t *out) {
     const int smem = t->stride * 8;
     cudaStream_t s = t->ctx->stream;
     const StepVariant &sv = step_variant(t);
-    // 2 = ping-pong step: the last two CTAs of the grid are the selectors (at least one row CTA besides them)
-    const int fused_mode = (t->pingpong && t->lookahead && grid >= 3) ? 2 : 1;
+    // ping-pong step: the last two CTAs of the grid are the selectors
+    const bool pp = use_pp(t);
+    const int fused_mode = pp ? 2 : 1;
+    const step_fn_t step_fused = pp ? sv.fn_pp : sv.fn;
     const int nsteps = batch_steps(t, kind);
     cudaGraph_t g;
     CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -528,14 +537,14 @@ static int get_graph(jslp_tab *t, int eidx, int kind, cudaGraphExec_t *out) {
                 cfg.attrs = at; cfg.numAttrs = 1;
                 TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = fused_mode; const double *a3 = t->hd.prow; int a4 = t->stride;
                 void *args[] = {&a0, &a1, &a2, &a3, &a4};
-                cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args);
+                cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)step_fused, args);
                 if (le != cudaSuccess) {
                     cudaGraph_t junk;
                     cudaStreamEndCapture(s, &junk);
                     return fail(JSLP_E_CUDA, std::string("PDL launch: ") + cudaGetErrorString(le));
                 }
             } else {
-                sv.fn<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, fused_mode, t->hd.prow, t->stride);
+                step_fused<<<grid, sv.threads, smem, s>>>(t->d_T, t->d_rec, fused_mode, t->hd.prow, t->stride);
             }
         }
     } else {  // two kernels per pivot
@@ -801,27 +810,7 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
             int e = snapshot_copy(t, slot, true);
             if (e) return e;
         }
-        if (t->pdl == 2 && engine == 2) {
-            // experiment: plain stream launches chained by programmatic dependent launch (no graph)
-            const StepVariant &sv = step_variant(t);
-            const int grid = step_grid(t), smem = t->stride * 8;
-            const int fused_mode = (t->pingpong && t->lookahead && grid >= 3) ? 2 : 1;
-            k_batch_begin<<<1, 32, 0, s>>>(t->d_rec);
-            k_select<<<1, 512, 0, s>>>(t->d_T, t->d_rec, -1, -1);
-            for (int i = 0; i < batch_steps(t, kind); i++) {
-                cudaLaunchConfig_t cfg;
-                memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sv.threads);
-                cfg.dynamicSmemBytes = smem; cfg.stream = s;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                at[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = at; cfg.numAttrs = i > 0 ? 1 : 0;
-                TabDev *a0 = t->d_T; Rec *a1 = t->d_rec; int a2 = fused_mode; const double *a3 = t->hd.prow; int a4 = t->stride;
-                void *args[] = {&a0, &a1, &a2, &a3, &a4};
-                CK(cudaLaunchKernelExC(&cfg, (const void *)sv.fn, args));
-            }
-        } else {
+        {
             cudaGraphExec_t ge;
             int e = get_graph(t, eidx, kind, &ge);
             if (e) return e;

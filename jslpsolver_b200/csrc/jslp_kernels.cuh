@@ -101,6 +101,19 @@ struct MipOut {
 
 __device__ __forceinline__ bool nz16(double v) { return !(v >= -1e-16 && v <= 1e-16); }
 
+// IEEE fp64 division.  Inline in the step kernels (a call costs more than the expansion on their
+// latency-critical paths); the resident node kernel uses the out-of-line ddiv_z below.
+__device__ __forceinline__ double ddiv(double a, double b) { return a / b; }
+
+// One shared copy with a fast path for zero dividends: the compiler's expansion sends 0 / b to its slow
+// path (~420 cycles instead of ~125 on B200) and degenerate node tableaux are full of zeros;
+// 0 / b = 0 signed (a xor b) for every b that is neither 0 nor NaN.
+__device__ __noinline__ double ddiv_z(double a, double b) {
+    if (a == 0.0 && b == b && b != 0.0)
+        return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull);
+    return a / b;
+}
+
 __device__ __forceinline__ double ldg_cg(const double *p) { return __ldcg(p); }
 // GLOBAL = tableau lives in HBM/L2 and may just have been rewritten by other CTAs (bypass L1);
 // !GLOBAL = tableau lives in this CTA's shared memory (generic pointers, plain loads).
@@ -134,7 +147,7 @@ struct RedSmem {
 
 // (value,index) arg-min / arg-max over the CTA, lowest index wins ties; result on every thread.
 template <bool IS_MIN>
-__device__ VI block_reduce_vi(VI x, const VI init, RedSmem &s) {
+__device__ __forceinline__ VI block_reduce_vi(VI x, const VI init, RedSmem &s) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         VI y;
@@ -159,7 +172,7 @@ __device__ VI block_reduce_vi(VI x, const VI init, RedSmem &s) {
 
 // op: 0 = min, 1 = sum
 template <int OP>
-__device__ int block_reduce_int(int x, RedSmem &s) {
+__device__ __forceinline__ int block_reduce_int(int x, RedSmem &s) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const int y = __shfl_xor_sync(0xffffffffu, x, o);
@@ -236,8 +249,8 @@ __device__ __forceinline__ void cta_copy_row(double *dst, const double *src, int
 // applied: the single-element form of update_rows for row 0.  v = raw pivot-row entry.
 __device__ __forceinline__ double priced_cost(double cost, double v, double coef0, bool nzc, bool is_pc, double q) {
     if (nzc) {
-        if (is_pc) return -coef0 / q;
-        const double f = nz16(v) ? v / q : 0.0;
+        if (is_pc) return ddiv(-coef0, q);
+        const double f = nz16(v) ? ddiv(v, q) : 0.0;
         return nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
     }
     return (coef0 != 0.0 && is_pc) ? 0.0 : cost;
@@ -295,7 +308,7 @@ __device__ __forceinline__ void price_finish(const TabDev &T, SelSmem &s, const 
 }
 
 template <bool GLOBAL, bool PRICED>
-__device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *costsrc, const double *rowsrc, double q,
+__device__ __noinline__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *costsrc, const double *rowsrc, double q,
                                double coef0, int cstar, int new_label, int *found_out, int *neg_out) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int W = T.W;
@@ -330,7 +343,7 @@ __device__ void cta_price_scan(const TabDev &T, SelSmem &s, const double *costsr
 // Literal, single-thread restatement of the pricing loop with optional objectives
 // (simplex.ts:132-263).  Only models with constraint weight/priority have them (tiny fixtures),
 // so the rare path trades speed for an exact transcription of the list semantics.
-__device__ void price_with_optional_seq(const TabDev &T, int *outCol, int *outNeg) {
+__device__ __noinline__ void price_with_optional_seq(const TabDev &T, int *outCol, int *outNeg) {
     const double prec = T.prec;
     const double *cost = T.M;
     const int lastColumn = T.W - 1;
@@ -424,7 +437,7 @@ __device__ void cta_stage_pivot(const TabDev &T, Rec *rec, int phase, int rstar,
 // 38-76, phase2: 129-303) and stages it.  All tableau reads bypass L1 (__ldcg): in the fused
 // kernel this runs after other CTAs have just rewritten the tableau.
 template <bool GLOBAL>
-__device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
+__device__ __noinline__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int W = T.W, H = T.H;
     const size_t stride = (size_t)T.stride;
@@ -478,7 +491,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
                     if (c >= W) continue;
                     const double coef = kv[k];
                     if ((has_unres && is_unres(T, T.vcol[c])) || coef < -prec) {
-                        const double quo = -cv[k] / coef;
+                        const double quo = ddiv(-cv[k], coef);
                         if (e.v < quo) { e.v = quo; e.i = c; }
                     }
                 }
@@ -535,7 +548,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
                 if (r == 0) continue;
                 if (-prec < col && col < prec) continue;
                 if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
-                const double quo = isneg ? -rhs / col : rhs / col;
+                const double quo = ddiv(isneg ? -rhs : rhs, col);
                 if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
             }
         }
@@ -573,7 +586,7 @@ __device__ void cta_select(const TabDev &T, Rec *rec, SelSmem &s) {
     cta_stage_pivot<GLOBAL>(T, rec, phase, rstar, cstar, isneg, cnt);
 }
 
-__device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s);
+__device__ __noinline__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s);
 
 // Standalone selection (engine 1, the first pivot of every solve, and Tableau.pivot()).
 // force_r/force_c >= 0: stage exactly that pivot (== Tableau.pivot(r, c)).

@@ -97,15 +97,6 @@ __device__ __forceinline__ VI warp_reduce_vi(VI x) {
 // an improving column, arg-max inside it, lowest column on ties.  Returns the column (0 = none).
 // One copy each of the bulky helpers: the pivot loop has to stay inside the instruction cache (an
 // earlier fully-inlined build had a 64 KB loop body and spent most of its time fetching instructions).
-// IEEE division.  A zero dividend sends the compiler's division to its slow path (~420 cycles
-// instead of ~125 on B200) and degenerate tableaux are full of zeros, so that case is answered
-// directly: 0 / b = 0 with the sign of a xor b for every b that is neither 0 nor NaN.
-__device__ __noinline__ double node_div(double a, double b) {
-    if (a == 0.0 && b == b && b != 0.0)
-        return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull);
-    return a / b;
-}
-
 __device__ __noinline__ int warp_price(const TabDev &T, const double *cost, const int *vcol, int W, int lane, int *neg_out) {
     const int bsz = T.use_partial ? T.batch_size : max(1, W - 1);
     const bool has_unres = T.unres != nullptr;
@@ -283,7 +274,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
             for (int c = 1 + tid; c < W; c += NT) {
                 const double coef = lrow[c];
                 if ((has_unres && is_unres(T, vcol[c])) || coef < -prec) {
-                    const double quo = node_div(-cost[c], coef);
+                    const double quo = ddiv_z(-cost[c], coef);
                     if (e.v < quo) { e.v = quo; e.i = c; }
                 }
             }
@@ -301,7 +292,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
                 if (r == 0) continue;
                 if (-prec < col && col < prec) continue;
                 if (col > 0 && prec > rv && rv > -prec) { dmin = min(dmin, r); continue; }
-                const double quo = node_div(neg ? -rv : rv, col);  // (-rhs) / col == -rhs / col
+                const double quo = ddiv_z(neg ? -rv : rv, col);  // (-rhs) / col == -rhs / col
                 if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
             }
             dmin = __reduce_min_sync(0xffffffffu, dmin);
@@ -371,7 +362,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
 #pragma unroll 1
             for (int c = tid; c < W; c += NT / 2) {
                 const double v = praw[c];
-                double f = (c == pcs || nz16(v)) ? node_div(c == pcs ? 1.0 : v, q) : 0.0;
+                double f = (c == pcs || nz16(v)) ? ddiv_z(c == pcs ? 1.0 : v, q) : 0.0;
                 if (flush && !nz16(f) && f != 0.0) f = 0.0;
                 frow[c] = f;
             }
@@ -382,7 +373,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
                 double *e = Ms + (size_t)slot[r] * Ws + pcs;
                 const double coef = *e;
                 pcol[r] = coef;
-                if (nz16(coef)) *e = node_div(-coef, q);
+                if (nz16(coef)) *e = ddiv_z(-coef, q);
                 else if (coef != 0.0) *e = 0.0;
             }
         }

@@ -22,7 +22,7 @@
 // to pricing afterwards; one L2 round trip whatever the number of pricing batches.
 
 // Generic entry: the pivot is already staged (prow side buffer, labels swapped, rec filled).
-__device__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
+__device__ __noinline__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &s) {
     const int cstar = rec->c;
     const double q = rec->q;
     const double coef0 = ldg_cg(T.M + cstar);
@@ -37,7 +37,7 @@ __device__ __forceinline__ double2 upd2(double2 old, double2 f, bool z0, bool z1
     if (z0) nv.x = __dsub_rn(old.x, __dmul_rn(coef, f.x));
     if (z1) nv.y = __dsub_rn(old.y, __dmul_rn(coef, f.y));
     if (pc) {
-        const double pv = -coef / q;  // simplex.ts:385
+        const double pv = ddiv(-coef, q);  // simplex.ts:385
         if (codd) nv.y = pv; else nv.x = pv;
     }
     return nv;
@@ -47,7 +47,7 @@ __device__ __forceinline__ double2 upd2(double2 old, double2 f, bool z0, bool z1
 // RC rows are processed together (RC independent 128-bit loads in flight per thread); PF adds a
 // software prefetch of the next column pair's RC loads before the current pair is stored.
 template <int RC, bool PF>
-__device__ __forceinline__ void update_rows(const TabDev &T, const double *frow, int r0, int nr, int rstar,
+__device__ __noinline__ void update_rows(const TabDev &T, const double *frow, int r0, int nr, int rstar,
                                             int cstar, double q, bool do_opt) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const size_t stride = (size_t)T.stride;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void update_rows(const TabDev &T, const double *frow,
                 double v = rc[c];
                 bool wr = false;
                 if (v0 != 0.0) { v = __dsub_rn(v, __dmul_rn(coefficient, v0)); wr = true; }
-                if (c == cstar) { v = -coefficient / q; wr = true; }
+                if (c == cstar) { v = ddiv(-coefficient, q); wr = true; }
                 if (wr) rc[c] = v;
             }
         }
@@ -144,7 +144,7 @@ __device__ __forceinline__ void update_rows(const TabDev &T, const double *frow,
 __device__ __forceinline__ double new_entry(double old, bool is_prow, double coef, double f, bool is_pc, double q) {
     if (is_prow) return f;
     if (nz16(coef)) {
-        if (is_pc) return -coef / q;
+        if (is_pc) return ddiv(-coef, q);
         return nz16(f) ? __dsub_rn(old, __dmul_rn(coef, f)) : old;
     }
     return (coef != 0.0 && is_pc) ? 0.0 : old;
@@ -166,7 +166,7 @@ __device__ __forceinline__ void cta_ratio_partial(const TabDev &T, SelSmem &s, i
         if (r != 0 && !(-prec < col && col < prec)) {
             if (col > 0 && prec > rhs && rhs > -prec) dmin = r;
             else {
-                const double quo = isneg ? -rhs / col : rhs / col;
+                const double quo = ddiv(isneg ? -rhs : rhs, col);
                 if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
             }
         }
@@ -181,7 +181,7 @@ __device__ __forceinline__ void cta_ratio_partial(const TabDev &T, SelSmem &s, i
 
 // ---- tail (look-ahead): reduce the partials, stage the next pivot, price the one after it -------
 // Two dependent L2 round trips: (1) the partials, (2) everything that depends on the leaving row.
-__device__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G, int cn, int isneg, int log_n) {
+__device__ __noinline__ void cta_tail_lookahead(const TabDev &T, Rec *rec, SelSmem &s, int G, int cn, int isneg, int log_n) {
     const int tid = threadIdx.x, NT = blockDim.x;
     if (cn == 0) {  // nothing prices in: optimal (simplex.ts:265-269); setEvaluation is done on the host
         if (tid == 0) { rec->status = ST_OPTIMAL; rec->phase = 2; rec->has_pivot = 0; rec->eval_raw = ldg_cg(T.M); }
@@ -369,7 +369,7 @@ __device__ __forceinline__ bool part_try_read(const Part *slot, unsigned int seq
 
 // Selector side: wait for all G partials of this launch and reduce them (simplex.ts:271-296 over the
 // whole column).  Returns false on a watchdog timeout (a lost publication must not hang the GPU).
-__device__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigned int seq, int *rnext, int *cnt_out) {
+__device__ __forceinline__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigned int seq, int *rnext, int *cnt_out) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int base = T.H / G, rem = T.H % G;
     VI m = {INFINITY, INT_MAX};
@@ -418,7 +418,7 @@ __device__ bool cta_collect_partials(const TabDev &T, SelSmem &s, int G, unsigne
 
 // Selector S1 of a ping-pong step: decides the next pivot, prices the one after it, writes the
 // record, swaps the labels and flips the descriptor.  frow = normalised row of the executing pivot.
-__device__ void cta_selector_decide(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
+__device__ __forceinline__ void cta_selector_decide(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
                                     int rstar, int cstar, double q, int cn, int isneg, int launch, int p2, int log_n,
                                     bool stop_after, long long *ts) {
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -549,16 +549,17 @@ __device__ __forceinline__ void part_wait(const Part *slot, unsigned int seq) {
     }
 }
 
-// Selector of a ping-pong step that executes a PHASE-1 pivot (rstar, cstar, q).  The row CTAs publish,
+// Selector of a ping-pong step that executes a PHASE-1 pivot (rstar, cstar, q), or a phase-2 pivot whose
+// successor has not been priced.  In phase 1 the row CTAs publish,
 // before they stream, the most negative right-hand side their rows will have after this pivot; this
 // CTA reduces those to the next leaving row (simplex.ts:38-54), derives that row and the cost row as
 // this pivot leaves them from the OLD tableau (new_entry), picks the entering column (56-76), counts
 // the non-zero entries of the next pivot column (lazy-flush flag), stages the next pivot row already
 // normalised and flips the descriptor -- all while the row CTAs stream.  When no infeasible row is
 // left it opens phase 2 itself (pricing 129-269, ratio test 271-296), again from derived values.
-__device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
-                                       int rstar, int cstar, double q, int launch, int p1, int log_n, bool stop_after,
-                                       int only_phase) {
+__device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G,
+                                         int rstar, int cstar, double q, int launch, int phase_exec, int pcount,
+                                         int log_n, bool stop_after, int only_phase) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const double *src = T.M;
     const size_t stride = (size_t)T.stride;
@@ -571,7 +572,8 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
         Tp->M2 = T.M;
     };
     auto finish = [&](int status, int phase, int unb) {  // no further pivot: final record (tid 0 only)
-        rec->done = launch + 1; rec->p1 = p1 + 1; rec->has_pivot = 0;
+        rec->done = launch + 1; rec->has_pivot = 0;
+        if (phase_exec == 1) rec->p1 = pcount + 1; else rec->p2 = pcount + 1;
         if (status != ST_RUNNING) {
             rec->status = status;
             if (phase) rec->phase = phase;
@@ -584,8 +586,10 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
         if (tid == 0) finish(ST_RUNNING, 0, -1);
         return;
     }
-    int rnext, cnt_unused;
-    if (!cta_collect_partials(T, s, G, seq, &rnext, &cnt_unused)) {
+    // A phase-2 pivot without a priced successor (the first phase-2 pivot of a solve) has no partials:
+    // the next pivot is derived below exactly as when phase 1 ends.
+    int rnext = -1, cnt_unused;
+    if (phase_exec == 1 && !cta_collect_partials(T, s, G, seq, &rnext, &cnt_unused)) {
         if (tid == 0) { rec->status = ST_ERROR; rec->has_pivot = 0; }
         return;
     }
@@ -613,7 +617,7 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
                 const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
                 if ((has_unres && is_unres(T, T.vcol[c])) || ur < -prec) {
                     const double uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
-                    const double quo = -uc / ur;
+                    const double quo = ddiv(-uc, ur);
                     if (e.v < quo) { e.v = quo; e.i = c; }
                 }
             }
@@ -642,8 +646,8 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
         }
         cnt = block_reduce_int<1>(cnt, s.red);
     } else {
-        // ---- feasible after this pivot (simplex.ts:51-54)
-        if (only_phase == 1) {
+        // ---- feasible after this pivot (simplex.ts:51-54), or already in phase 2
+        if (phase_exec == 1 && only_phase == 1) {
             if (tid == 0) finish(ST_P1_DONE, 0, -1);
             return;
         }
@@ -701,7 +705,7 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
                 if (r == 0) continue;
                 if (-prec < col && col < prec) continue;
                 if (col > 0 && prec > rhs && rhs > -prec) { dmin = min(dmin, r); continue; }
-                const double quo = isneg ? -rhs / col : rhs / col;
+                const double quo = ddiv(isneg ? -rhs : rhs, col);
                 if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
             }
         }
@@ -737,8 +741,7 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
             double f = 0.0;
             if (c < W) {
                 const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
-                f = nz16(ur) ? ur / qn : 0.0;
-                if (c == cn) f = 1.0 / qn;
+                f = (c == cn || nz16(ur)) ? ddiv(c == cn ? 1.0 : ur, qn) : 0.0;
                 if (flushn && !nz16(f) && f != 0.0) f = 0.0;
             }
             T.prow[c] = f;
@@ -750,7 +753,8 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
         rec->log_n = log_n + 1;
         T.vrow[rnext] = entering;  // simplex.ts:339-349
         T.vcol[cn] = leaving;
-        rec->done = launch + 1; rec->p1 = p1 + 1;
+        rec->done = launch + 1;
+        if (phase_exec == 1) rec->p1 = pcount + 1; else rec->p2 = pcount + 1;
         rec->phase = phase_next; rec->r = rnext; rec->c = cn; rec->q = qn; rec->is_neg = isneg;
         rec->flush = flushn;
         rec->has_pivot = 1;
@@ -763,7 +767,7 @@ __device__ void cta_selector_decide_p1(TabDev *Tp, const TabDev &T, Rec *rec, Se
 
 // Selector S2 of a ping-pong step: stages the raw pivot row of the next pivot (the row as the
 // executing pivot leaves it) into the prow side buffer, the TMA source of the next launch.
-__device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G, int rstar,
+__device__ __forceinline__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const double *frow, int G, int rstar,
                                    int cstar, double q, int cn, int launch, bool stop_after) {
     const int tid = threadIdx.x, NT = blockDim.x;
     if (cn == 0 || stop_after) return;
@@ -802,8 +806,7 @@ __device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const 
             double f = 0.0;
             if (c < T.W) {
                 const double ur = new_entry(rv[k], is_prow, coef_r, frow[c], c == cstar, q);
-                f = nz16(ur) ? ur / qn : 0.0;
-                if (c == cn) f = 1.0 / qn;
+                f = (c == cn || nz16(ur)) ? ddiv(c == cn ? 1.0 : ur, qn) : 0.0;
                 if (flushn && !nz16(f) && f != 0.0) f = 0.0;
             }
             T.prow[c] = f;
@@ -818,7 +821,7 @@ __device__ void cta_selector_stage(const TabDev &T, Rec *rec, SelSmem &s, const 
 // ping-pong path (phase 1, bootstrap, optional objectives) run in place on the first gridDim.x-2 CTAs.
 // prow_arg / stride_arg duplicate TabDev.prow / stride (both immutable after jslp_tab_create) so the
 // TMA copy of the pivot row can be issued before the descriptor has been fetched.
-template <int NTHREADS, int MINB, int RC, bool PF>
+template <int NTHREADS, int MINB, int RC, bool PF, bool PP>
 __global__ void __launch_bounds__(NTHREADS, MINB)
     k_pivot_step(TabDev *Tp, Rec *rec, int do_select, const double *prow_arg, int stride_arg) {
     extern __shared__ __align__(128) double frow[];
@@ -858,21 +861,25 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     if (dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
 
     const int b = blockIdx.x;
-    const int G = do_select == 2 ? (int)gridDim.x - 2 : (int)gridDim.x;  // row CTAs (ping-pong: + 2 selector CTAs)
+    const int G = PP ? (int)gridDim.x - 2 : (int)gridDim.x;  // row CTAs (ping-pong: + 2 selector CTAs)
     const int base = T.H / G, rem = T.H % G;
     const int r0 = b * base + min(b, rem);
     const int nr = b < G ? base + (b < rem ? 1 : 0) : 0;
     const bool rows_fit = base + 1 <= NT;  // one row per thread in the look-ahead (uniform over the grid)
 
+    if constexpr (PP) {
     // ------------------------------------------------------------------ ping-pong path
     // Grid = G row CTAs + 2 selector CTAs (decide, stage).  Eligible: phase 2 with the next entering
     // column already priced, no optional objectives, at most 32 rows per CTA (one warp runs the
     // look-ahead ratio test of the CTA's rows).
-    const bool pp_ok = do_select == 2 && T.nOpt == 0 && T.M2 != nullptr && base + 1 <= 32;
-    const bool pp1 = pp_ok && phase == 1;                 // phase-1 pivot: the selector decides everything
-    const bool pp = pp1 || (pp_ok && next_c >= 0 && phase == 2);
-    if (pp) {
-        const bool want_partial = pp1 ? !stop_after : (next_c > 0 && !stop_after);
+    // pp2: phase-2 pivot whose successor's entering column is priced (the steady state): row CTAs publish
+    //      ratio-test partials, selector S1 decides from them, selector S2 stages the next pivot row.
+    // pp1: phase-1 pivot: row CTAs publish min-RHS partials, S1 decides and stages everything.
+    // pp0: phase-2 pivot without a priced successor: no partials, S1 derives the next pivot on its own.
+    const bool pp2 = phase == 2 && next_c >= 0;
+    const bool pp1 = phase == 1;
+    {
+        const bool want_partial = !stop_after && (pp1 || (pp2 && next_c > 0));
         const int lw = (NT >> 5) - 1;           // the warp that runs the look-ahead (last warp)
         const int lane = tid & 31;
         const bool la_warp = (tid >> 5) == lw && b < G;
@@ -896,7 +903,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                 // phase 1: the most negative right-hand side of this CTA's rows after this pivot
                 double f_0 = raw_0;
                 if (!prow_norm) {
-                    f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
+                    f_0 = nz16(raw_0) ? ddiv(raw_0, q) : 0.0;
                     if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
                 }
                 const bool is_prow = (r0 + lane) == rstar;
@@ -918,10 +925,9 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             } else if (want_partial) {
                 double f_n = raw_n, f_0 = raw_0;
                 if (!prow_norm) {
-                    f_n = nz16(raw_n) ? raw_n / q : 0.0;
-                    if (next_c == cstar) f_n = 1.0 / q;
+                    f_n = (next_c == cstar || nz16(raw_n)) ? ddiv(next_c == cstar ? 1.0 : raw_n, q) : 0.0;
                     if (flush && !nz16(f_n) && f_n != 0.0) f_n = 0.0;
-                    f_0 = nz16(raw_0) ? raw_0 / q : 0.0;
+                    f_0 = nz16(raw_0) ? ddiv(raw_0, q) : 0.0;
                     if (flush && !nz16(f_0) && f_0 != 0.0) f_0 = 0.0;
                 }
                 const bool is_prow = (r0 + lane) == rstar;
@@ -936,7 +942,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                     if (r != 0 && !(-prec < col && col < prec)) {
                         if (col > 0 && prec > rhs && rhs > -prec) dmin = lane;
                         else {
-                            const double quo = next_neg ? -rhs / col : rhs / col;
+                            const double quo = ddiv(next_neg ? -rhs : rhs, col);
                             if (quo > prec && m.v > quo) { m.v = quo; m.i = lane; }
                         }
                     }
@@ -962,18 +968,18 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         if (!prow_norm) {
             for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
                 const double v = frow[c];
-                double f = nz16(v) ? v / q : 0.0;
-                if (c == cstar) f = 1.0 / q;
+                double f = (c == cstar || nz16(v)) ? ddiv(c == cstar ? 1.0 : v, q) : 0.0;
                 if (flush && !nz16(f) && f != 0.0) f = 0.0;
                 frow[c] = f;
             }
         }
         __syncthreads();
         if (dbg && tid == 0) t1 = clock64();
-        if (pp1 && b == G) {
-            cta_selector_decide_p1(Tp, T, rec, sel, frow, G, rstar, cstar, q, launch, p1, log_n0, stop_after, rec->only_phase);
+        if (!pp2 && b == G) {
+            cta_selector_decide_full(Tp, T, rec, sel, frow, G, rstar, cstar, q, launch, phase, phase == 1 ? p1 : p2, log_n0,
+                                     stop_after, rec->only_phase);
             if (dbg && tid == 0) t2 = t3 = clock64();
-        } else if (pp1 && b == G + 1) {
+        } else if (!pp2 && b == G + 1) {
             // idle in a phase-1 step; tells the deciding selector that its TMA read of prow has landed
             if (tid == 0) part_publish(T.part + G + 1, 0.0, 255, 255, 0, (unsigned int)(launch + 1));
             if (dbg && tid == 0) t2 = t3 = clock64();
@@ -1000,11 +1006,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         }
         return;
     }
-    if (b >= G) {  // the selector CTA has nothing to do in an in-place step
-        mbar_wait(&bar, 0);  // ... but must not exit with its TMA copy still in flight
-        return;
-    }
-
+    } else {
     // ------------------------------------------------------------------ in-place path
     // look-ahead operands of this thread's row, loaded while the TMA copy is in flight
     const bool fast = do_select && next_c >= 0 && !stop_after && rows_fit;
@@ -1021,8 +1023,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     if (!prow_norm) {
         for (int c = tid; c < T.stride; c += NT) {  // normalise in place (simplex.ts:352-364, 380-382)
             const double v = frow[c];
-            double f = nz16(v) ? v / q : 0.0;
-            if (c == cstar) f = 1.0 / q;
+            double f = (c == cstar || nz16(v)) ? ddiv(c == cstar ? 1.0 : v, q) : 0.0;
             if (flush && !nz16(f) && f != 0.0) f = 0.0;
             frow[c] = f;
         }
@@ -1073,5 +1074,6 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         long long *d = T.dbg + ((size_t)launch * T.dbg_grid + b) * 8;
         d[0] = g0; d[1] = t1 - t0; d[2] = t2 - t0; d[3] = t3 - t0; d[4] = t4 - t0; d[5] = smid; d[6] = s_last; d[7] = nr;
+    }
     }
 }
