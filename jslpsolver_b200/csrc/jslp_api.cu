@@ -441,6 +441,10 @@ static const StepVariant STEP_VARIANTS[] = {
     {JSLP_VARIANT(512, 1, 8, false), "t512 occ1 rc8"},
     {JSLP_VARIANT(256, 3, 4, true), "t256 occ3 rc4 prefetch"},
     {JSLP_VARIANT(128, 8, 4, false), "t128 occ8 rc4"},
+    {JSLP_VARIANT(256, 2, 4, false), "t256 occ2 rc4"},
+    {JSLP_VARIANT(256, 2, 2, true), "t256 occ2 rc2 prefetch"},
+    {JSLP_VARIANT(256, 1, 8, false), "t256 occ1 rc8"},
+    {JSLP_VARIANT(512, 1, 4, false), "t512 occ1 rc4"},
 };
 static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VARIANTS[0]));
 static const int SMALL_BATCH = 24;  // steps in the first graph of a solve
@@ -783,6 +787,7 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     init.only_phase = only_phase;
     init.lookahead = (engine == 2 && t->lookahead && t->nOpt == 0) ? 1 : 0;
     init.next_c = -1;
+    init.pad1 = t->pdl == 2 ? 1 : 0;  // experiment switch (JSLP_OPT_PDL = 2)
     *t->h_rec = init;
     if (timed) CK(cudaEventRecord(ctx->ev0, s));
     CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));

@@ -18,6 +18,7 @@
 //                 NEXT pivot, so one launch == one simplex iteration and a CUDA graph of N launches
 //                 needs no host round trip.  Memory-bound (0.125 flop/B): no tensor cores.
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <limits.h>
@@ -92,6 +93,10 @@ struct Rec {
     double q;        // raw pivot element
     double eval_raw; // matrix[0] at exit
 };
+
+// k_pivot_step reads the record with 16-byte loads
+static_assert(offsetof(Rec, c) == 16 && offsetof(Rec, p1) == 32 && offsetof(Rec, unbounded_var) == 48 && offsetof(Rec, lookahead) == 64 &&
+              offsetof(Rec, q) == 88, "Rec layout");
 
 struct MipOut {
     int is_integral;

@@ -837,9 +837,9 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     // when the launch carries no programmatic dependency.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
-    const int status = rec->status, has_pivot = rec->has_pivot, stop_at = rec->stop_at, launch = rec->done;
-    if (status != ST_RUNNING || !has_pivot) return;
-    if (stop_at >= 0 && launch >= stop_at) return;
+    // The head is one L2 round trip deep: the TMA copy of the pivot row needs only kernel parameters and
+    // goes first; the record (one 128-byte line) and the descriptor are requested together, before the
+    // first value is looked at.
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, g0 = 0;
     if (tid == 0) {
         t0 = clock64();
@@ -847,14 +847,23 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         mbar_init(&bar, 1);
         fence_mbar_init();
         mbar_expect_tx(&bar, (uint32_t)stride_arg * 8u);
-        tma_bulk_g2s(frow, prow_arg, (uint32_t)stride_arg * 8u, &bar);  // raw pivot row -> smem (TMA)
-        T = *Tp;
+        tma_bulk_g2s(frow, prow_arg, (uint32_t)stride_arg * 8u, &bar);  // pivot row -> smem (TMA)
     }
-    const int rstar = rec->r, cstar = rec->c, flush = rec->flush, phase = rec->phase;
-    const int p1 = rec->p1, p2 = rec->p2, log_n0 = rec->log_n;
+    const int4 *rp = reinterpret_cast<const int4 *>(rec);
+    // plain (L1-cached) loads: 2368 warps read this one line, L1 serves all but the first per SM
+    const int4 ra = rp[0], rb = rp[1], rc = rp[2], rd = rp[3], re = rp[4];
     const double q = rec->q;
-    const int next_c = rec->next_c, next_neg = rec->next_neg, lookahead = rec->lookahead;
-    const int prow_norm = rec->prow_norm;
+    const int gate = rec->pad1;  // experiment: hold the streaming warps until the partial is published
+    if (tid == 0) T = *Tp;
+    const int status = ra.x, phase = ra.y, has_pivot = ra.z, rstar = ra.w;
+    const int cstar = rb.x, flush = rb.z, launch = rb.w;
+    const int p1 = rc.x, p2 = rc.y, stop_at = rc.z, log_n0 = rc.w;
+    const int only_phase = rd.y;
+    const int lookahead = re.x, next_c = re.y, next_neg = re.z, prow_norm = re.w;
+    if (status != ST_RUNNING || !has_pivot || (stop_at >= 0 && launch >= stop_at)) {
+        if (tid == 0) mbar_wait(&bar, 0);  // do not exit with the TMA copy still in flight
+        return;
+    }
     const bool stop_after = stop_at >= 0 && launch + 1 >= stop_at;
     __syncthreads();
     const bool dbg = T.dbg != nullptr && launch < T.dbg_cap;
@@ -964,6 +973,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                 }
             }
         }
+        if (gate && la_warp) __syncwarp();
         mbar_wait(&bar, 0);
         if (!prow_norm) {
             for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
@@ -977,7 +987,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
         if (dbg && tid == 0) t1 = clock64();
         if (!pp2 && b == G) {
             cta_selector_decide_full(Tp, T, rec, sel, frow, G, rstar, cstar, q, launch, phase, phase == 1 ? p1 : p2, log_n0,
-                                     stop_after, rec->only_phase);
+                                     stop_after, only_phase);
             if (dbg && tid == 0) t2 = t3 = clock64();
         } else if (!pp2 && b == G + 1) {
             // idle in a phase-1 step; tells the deciding selector that its TMA read of prow has landed
