@@ -94,14 +94,25 @@ static void from_wire(NodeEval &e, const double *w) {
 // HBM path: applyCuts (branch-and-cut.ts:33-52) in place, exactly as the reference does it.
 static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check_cycles, jslp_bnb::NodeEval &ev) {
     jslp_lp_status st;
+    static const bool dbg = getenv("JSLP_DEBUG") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b2) {
+        return std::chrono::duration<double, std::micro>(b2 - a).count();
+    };
+    const auto t_0 = tnow();
     int rc = jslp_restore(t);
     if (rc) return rc;
+    if (dbg) cudaStreamSynchronize(t->ctx->stream);
+    const auto t_1 = tnow();
     rc = jslp_add_cuts(t, b.cuts.data(), (int)b.cuts.size());
     if (rc) return rc;
+    if (dbg) cudaStreamSynchronize(t->ctx->stream);
+    const auto t_2 = tnow();
     const double prevBest = t->bestPossibleEval;
     const int prevIters = t->simplexIters;
     rc = run_lp(t, 0, check_cycles, &st, false);
     if (rc) return rc;
+    const auto t_3 = tnow();
     // simplexIters / bestPossibleEval are frontier state: the commit loop owns them
     ev.optimal = t->simplexIters != prevIters;
     t->simplexIters = prevIters;
@@ -122,6 +133,9 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
             for (int o = 0; o < t->nOpt && o < 7; o++) ev.opt0[o] = opt[(size_t)o * t->W];
         }
     }
+    if (dbg)
+        fprintf(stderr, "stream node: cuts %d pivots %d+%d restore %.0f us add_cuts %.0f us run_lp %.0f us rest %.0f us\n",
+                (int)b.cuts.size(), st.phase1_pivots, st.phase2_pivots, us(t_0, t_1), us(t_1, t_2), us(t_2, t_3), us(t_3, tnow()));
     return JSLP_OK;
 }
 

@@ -586,6 +586,8 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
         if (tid == 0) finish(ST_RUNNING, 0, -1);
         return;
     }
+    if (tid == 0) part_wait(T.part + G + 1, seq);  // the other selector's TMA read of prow has landed (it is
+                                                   // published within the first microsecond: no wait later)
     // A phase-2 pivot without a priced successor (the first phase-2 pivot of a solve) has no partials:
     // the next pivot is derived below exactly as when phase 1 ends.
     int rnext = -1, cnt_unused;
@@ -595,8 +597,102 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
     }
     int phase_next = 1, cn = 0, isneg = 0, cnt = 0;
     const bool has_unres = T.unres != nullptr;
+    if (rnext >= 0 && T.stride <= 8 * NT) {
+        // ---- phase 1 goes on, fast path (two L2 round trips after the partials): the whole derived row
+        // rnext fits in eight registers per thread, so the entering-column scan (simplex.ts:56-76), the
+        // pivot element and the normalised row staged for the next launch all come from ONE set of loads.
+        const double *rowp = src + (size_t)rnext * stride;
+        const bool is_prow = rnext == rstar;
+        const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
+        const int leaving = T.vrow[rnext];
+        double ur[8], cv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = tid + k * NT;
+            ur[k] = c < W ? ldg_cg(rowp + c) : 0.0;
+            cv[k] = c < W ? ldg_cg(src + c) : 0.0;
+        }
+        const VI einit = {-INFINITY, INT_MAX};
+        VI e = einit;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = tid + k * NT;
+            if (c >= W) continue;
+            ur[k] = new_entry(ur[k], is_prow, coef_r, frow[c], c == cstar, q);
+            if (c >= 1 && ((has_unres && is_unres(T, T.vcol[c])) || ur[k] < -prec)) {
+                const double uc = new_entry(cv[k], false, coef0, frow[c], c == cstar, q);
+                const double quo = ddiv(-uc, ur[k]);
+                if (e.v < quo) { e.v = quo; e.i = c; }
+            }
+        }
+        e = block_reduce_vi<false>(e, einit, s.red);
+        if (e.i == INT_MAX) {  // simplex.ts:73-76
+            if (tid == 0) finish(ST_INFEASIBLE, 0, -1);
+            return;
+        }
+        cn = e.i;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (tid + k * NT == cn) {  // the owner of column cn publishes the pivot element and the cost-row entry
+                s.bq = ur[k];
+                s.bc0 = new_entry(cv[k], false, coef0, frow[cn], cn == cstar, q);
+            }
+        __syncthreads();
+        const double qn = s.bq;
+        // Lazy-flush flag (simplex.ts:380): does any row other than rnext hold a non-zero entry in column
+        // cn?  The cost row and the executing pivot's row are witnesses that cost nothing; only when
+        // both are zero is the whole column derived and counted.
+        bool flushn = nz16(s.bc0) || (rstar != rnext && nz16(frow[cn]));
+        if (!flushn) {
+            const double f_cn = frow[cn];
+            for (int rb = 0; rb < H; rb += 8 * NT) {
+                double a[8], cf[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int r = rb + tid + k * NT;
+                    a[k] = r < H ? ldg_cg(src + (size_t)r * stride + cn) : 0.0;
+                    cf[k] = (r < H && r != rstar) ? ldg_cg(src + (size_t)r * stride + cstar) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int r = rb + tid + k * NT;
+                    if (r < H && nz16(new_entry(a[k], r == rstar, cf[k], f_cn, cn == cstar, q))) cnt++;
+                }
+            }
+            cnt = block_reduce_int<1>(cnt, s.red);
+            flushn = (cnt - (nz16(qn) ? 1 : 0)) > 0;
+        }
+        const int entering = T.vcol[cn];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = tid + k * NT;
+            if (c >= T.stride) continue;
+            double f = 0.0;
+            if (c < W) {
+                f = (c == cn || nz16(ur[k])) ? ddiv(c == cn ? 1.0 : ur[k], qn) : 0.0;
+                if (flushn && !nz16(f) && f != 0.0) f = 0.0;
+            }
+            T.prow[c] = f;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rnext, cn, leaving, entering);
+            rec->log_n = log_n + 1;
+            T.vrow[rnext] = entering;  // simplex.ts:339-349
+            T.vcol[cn] = leaving;
+            rec->done = launch + 1; rec->p1 = pcount + 1;
+            rec->phase = 1; rec->r = rnext; rec->c = cn; rec->q = qn; rec->is_neg = 0;
+            rec->flush = flushn ? 1 : 0;
+            rec->has_pivot = 1;
+            rec->next_c = -1;    // the pivot after this one has not been priced
+            rec->prow_norm = 1;  // the row above is already normalised
+            __threadfence();     // prow and the record are read by the next launch
+            flip();
+        }
+        return;
+    }
     if (rnext >= 0) {
-        // ---- phase 1 goes on: entering column of row rnext (simplex.ts:56-76) on derived entries
+        // ---- phase 1 goes on (wide tableau: more than eight columns per thread), same steps with reloads
         const double *rowp = src + (size_t)rnext * stride;
         const bool is_prow = rnext == rstar;
         const double coef_r = is_prow ? 0.0 : ldg_cg(rowp + cstar);
@@ -725,7 +821,6 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
     const bool flushn = (cnt - (nz16(qn) ? 1 : 0)) > 0;
     const int leaving = T.vrow[rnext];
     const int entering = T.vcol[cn];
-    if (tid == 0) part_wait(T.part + G + 1, seq);  // the other selector's TMA read of prow has landed
     __syncthreads();
     for (int c0 = 0; c0 < T.stride; c0 += 8 * NT) {
         double rv[8];
