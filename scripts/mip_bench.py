@@ -47,9 +47,12 @@ def main():
     mk = int(os.environ.get("KNAP_CONS", "512"))
     knap_nodes = int(os.environ.get("KNAP_NODES", "120"))
     knap = problems.knapsack_mip_model(nk, mk, seed=12345)
-    workloads = [("LargeFarmMIP (36x101 root, tolerance 0.005)", farm, 0),
+    workloads = [] if os.environ.get("NO_FARM", "0") == "1" else [("LargeFarmMIP (36x101 root, tolerance 0.005)", farm, 0)]
+    workloads += [
                  (f"knapsack {nk} binaries x {mk} constraints (root {nk + mk + 1}x{nk + 1}), first {knap_nodes} nodes",
                   knap, knap_nodes)]
+    if os.environ.get("NO_KNAP", "0") == "1":
+        workloads = workloads[:-1]
     widths = [int(x) for x in os.environ.get("SPEC", "1,8,32,128").split(",")]
     spin = torch.zeros(1 << 26, device="cuda")
     for name, model, max_nodes in workloads:
@@ -94,6 +97,15 @@ def main():
                        "host_eval_ms": b.host_eval_ms, "host_commit_ms": b.host_commit_ms,
                        "host_root_ms": b.host_root_ms, "host_final_ms": b.host_final_ms,
                        "node_kernel_ms": b.node_kernel_ms}
+                # node phase = everything after the (unsharded) root relaxation
+                tot = torch.tensor([float(b.nodes_evaluated)], device="cpu" if one_gpu else "cuda")
+                if world > 1:
+                    torch.distributed.all_reduce(tot)
+                node_ms = b.host_eval_ms - b.host_root_ms + b.host_commit_ms
+                rec["node_lps_all_ranks"] = int(tot.item())
+                rec["node_phase_ms"] = node_ms
+                rec["node_phase_node_lps_per_s"] = (int(tot.item()) - world) / (node_ms * 1e-3) if node_ms > 0 else None
+                rec["node_phase_committed_per_s"] = (b.iterations - 1) / (node_ms * 1e-3) if node_ms > 0 else None
                 if best is None or rec["gpu_ms"] < best["gpu_ms"]:
                     best = rec
             if rank == 0:
