@@ -399,7 +399,7 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
             t->pingpong = value != 0;
             return JSLP_OK;
         case JSLP_OPT_PDL:
-            t->pdl = (int)value;  // 1 = PDL edges inside the graph, 2 = PDL-chained plain launches
+            t->pdl = value != 0;  // programmatic-dependent-launch edges inside the graph (measured: no gain)
             return JSLP_OK;
         case JSLP_OPT_TIMELINE:
             if (value < 0 || value > 4096) return fail(JSLP_E_INVALID, "timeline launches must be 0..4096");
@@ -787,7 +787,6 @@ static int run_lp(jslp_tab *t, int only_phase, int check_cycles, jslp_lp_status 
     init.only_phase = only_phase;
     init.lookahead = (engine == 2 && t->lookahead && t->nOpt == 0) ? 1 : 0;
     init.next_c = -1;
-    init.pad1 = t->pdl == 2 ? 1 : 0;  // experiment switch (JSLP_OPT_PDL = 2)
     *t->h_rec = init;
     if (timed) CK(cudaEventRecord(ctx->ev0, s));
     CK(cudaMemcpyAsync(t->d_rec, t->h_rec, sizeof(Rec), cudaMemcpyHostToDevice, s));

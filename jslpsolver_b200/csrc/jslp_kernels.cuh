@@ -196,6 +196,70 @@ __device__ __forceinline__ int block_reduce_int(int x, RedSmem &s) {
     return x;
 }
 
+__device__ __forceinline__ unsigned long long dkey(double v) {  // order-preserving for non-NaN, -0 == +0
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// (value, index) arg-min / arg-max over the warp, lowest index on ties; x.v must not be NaN.
+template <bool IS_MIN>
+__device__ __forceinline__ VI warp_reduce_vi(VI x) {
+    const unsigned long long k = dkey(x.v);
+    const unsigned int hi = (unsigned int)(k >> 32), lo = (unsigned int)k;
+    unsigned int mhi, mlo;
+    if (IS_MIN) {
+        mhi = __reduce_min_sync(0xffffffffu, hi);
+        mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    } else {
+        mhi = __reduce_max_sync(0xffffffffu, hi);
+        mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    }
+    VI r;
+    r.i = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? x.i : INT_MAX);
+    r.v = dkey_inv(((unsigned long long)mhi << 32) | mlo);
+    return r;
+}
+
+
+// ---- CTA-wide reductions built on redux.sync (a third of the latency of the shuffle trees above; used on
+// the selectors' critical path).  Results on every thread; one trailing barrier protects s for reuse.
+template <bool IS_MIN>
+__device__ __forceinline__ VI block_reduce_vi_rx(VI x, const VI init, RedSmem &s) {
+    x = warp_reduce_vi<IS_MIN>(x);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) { s.v[w] = x.v; s.i[w] = x.i; }
+    __syncthreads();
+    VI y = init;
+    if (l < nw) { y.v = s.v[l]; y.i = s.i[l]; }
+    y = warp_reduce_vi<IS_MIN>(y);
+    __syncthreads();
+    return y;
+}
+
+// Ratio-test reduction: min first-degenerate row, (quotient,row) arg-min with lowest-row ties, count of
+// non-zero pivot-column entries, and an all-ok flag (min).
+__device__ __forceinline__ void block_reduce_ratio_rx(int &dmin, VI &m, int &cnt, int &ok, RedSmem &s) {
+    m = warp_reduce_vi<true>(m);
+    dmin = __reduce_min_sync(0xffffffffu, dmin);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    ok = __reduce_min_sync(0xffffffffu, ok);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) { s.v[w] = m.v; s.i[w] = m.i; s.a[w] = dmin; s.b[w] = cnt | (ok ? 0 : (1 << 30)); }
+    __syncthreads();
+    VI y = {INFINITY, INT_MAX};
+    int d = INT_MAX, n = 0, bad = 0;
+    if (l < nw) { y.v = s.v[l]; y.i = s.i[l]; d = s.a[l]; n = s.b[l] & ~(1 << 30); bad = (s.b[l] >> 30) & 1; }
+    m = warp_reduce_vi<true>(y);
+    dmin = __reduce_min_sync(0xffffffffu, d);
+    cnt = __reduce_add_sync(0xffffffffu, n);
+    ok = __reduce_max_sync(0xffffffffu, bad) ? 0 : 1;
+    __syncthreads();
+}
+
 __device__ __forceinline__ bool is_unres(const TabDev &T, int varIndex) {
     return T.unres != nullptr && varIndex >= 0 && varIndex < T.n_index && T.unres[varIndex] != 0;
 }
@@ -309,6 +373,35 @@ __device__ __forceinline__ void price_finish(const TabDev &T, SelSmem &s, const 
     __syncthreads();
     *found_out = found;
     *neg_out = found > 0 ? s.bc_neg : 0;
+    __syncthreads();
+}
+
+// price_finish on redux.sync: one lexicographic reduction (batch asc, value desc, column asc).
+__device__ __forceinline__ void price_finish_rx(const TabDev &T, SelSmem &s, const PriceAcc &a, int *found_out, int *neg_out) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    int b = a.myb, col = a.x.i, neg = a.myneg;
+    double v = a.x.v;
+#pragma unroll
+    for (int stage = 0; stage < 2; stage++) {
+        const int mb = __reduce_min_sync(0xffffffffu, b);
+        const bool in = b == mb && mb != INT_MAX;
+        const unsigned long long k = dkey(v);
+        const unsigned int hi = (unsigned int)(k >> 32), lo = (unsigned int)k;
+        const unsigned int mhi = __reduce_max_sync(0xffffffffu, in ? hi : 0u);
+        const unsigned int mlo = __reduce_max_sync(0xffffffffu, (in && hi == mhi) ? lo : 0u);
+        const bool win = in && hi == mhi && lo == mlo;
+        const int mc = __reduce_min_sync(0xffffffffu, win ? col : INT_MAX);
+        const int mn = __reduce_max_sync(0xffffffffu, (win && col == mc) ? neg : 0);
+        b = mb; col = mc; neg = mn; v = dkey_inv(((unsigned long long)mhi << 32) | mlo);
+        if (stage == 0) {
+            if (l == 0) { s.red.i[w] = b; s.red.v[w] = v; s.red.a[w] = col; s.red.b[w] = neg; }
+            __syncthreads();
+            if (l < nw) { b = s.red.i[l]; v = s.red.v[l]; col = s.red.a[l]; neg = s.red.b[l]; }
+            else { b = INT_MAX; v = T.prec; col = INT_MAX; neg = 0; }
+        }
+    }
+    *found_out = b == INT_MAX ? 0 : col;
+    *neg_out = b == INT_MAX ? 0 : neg;
     __syncthreads();
 }
 

@@ -65,34 +65,6 @@ __device__ __forceinline__ long long globaltimer_ns() {
 // every ~8 cycles, so the reductions avoid shuffle trees: values are mapped to order-preserving
 // integer keys and reduced with redux.sync (three to four REDUX per arg-min instead of five shuffle
 // levels of fp64 compares), and the scans issue their loads and divisions four at a time.
-__device__ __forceinline__ unsigned long long dkey(double v) {  // order-preserving for non-NaN, -0 == +0
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dkey_inv(unsigned long long k) {
-    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-    return __longlong_as_double((long long)b);
-}
-
-// (value, index) arg-min / arg-max over the warp, lowest index on ties; x.v must not be NaN.
-template <bool IS_MIN>
-__device__ __forceinline__ VI warp_reduce_vi(VI x) {
-    const unsigned long long k = dkey(x.v);
-    const unsigned int hi = (unsigned int)(k >> 32), lo = (unsigned int)k;
-    unsigned int mhi, mlo;
-    if (IS_MIN) {
-        mhi = __reduce_min_sync(0xffffffffu, hi);
-        mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-    } else {
-        mhi = __reduce_max_sync(0xffffffffu, hi);
-        mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-    }
-    VI r;
-    r.i = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? x.i : INT_MAX);
-    r.v = dkey_inv(((unsigned long long)mhi << 32) | mlo);
-    return r;
-}
-
 // Phase-2 pricing of the cost row (simplex.ts:140-219 without optional objectives): first batch with
 // an improving column, arg-max inside it, lowest column on ties.  Returns the column (0 = none).
 // One copy each of the bulky helpers: the pivot loop has to stay inside the instruction cache (an
@@ -222,7 +194,12 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
     int4 *plog = nb.logs + (size_t)node * nb.log_cap;
     const bool has_unres = T.unres != nullptr;
     long long cy[6] = {0, 0, 0, 0, 0, 0}, cprev = clock64();
+// per-phase cycle counters of warp 0 (S1, S2, S3, D, U, barrier): compile with -DJSLP_NODE_CYCLES to fill them
+#ifdef JSLP_NODE_CYCLES
 #define NODE_CY(k) do { const long long cnow = clock64(); cy[k] += cnow - cprev; cprev = cnow; } while (0)
+#else
+#define NODE_CY(k) do { (void)cprev; } while (0)
+#endif
     double *pcol = rhs;  // old pivot-column entries of the pivot in flight (the RHS copy is only made at the end)
 
     // One pivot = five CTA barriers.  fp64 division has a latency of several hundred cycles and does not

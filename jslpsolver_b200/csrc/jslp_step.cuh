@@ -408,9 +408,8 @@ __device__ __forceinline__ bool cta_collect_partials(const TabDev &T, SelSmem &s
             }
         }
     }
-    ok = block_reduce_int<0>(ok, s.red);
+    block_reduce_ratio_rx(dmin, m, cnt, ok, s.red);
     if (!ok) return false;
-    block_reduce_ratio(dmin, m, cnt, s.red);
     *rnext = dmin != INT_MAX ? dmin : (m.i != INT_MAX ? m.i : -1);
     *cnt_out = cnt;
     return true;
@@ -495,7 +494,7 @@ __device__ __forceinline__ void cta_selector_decide(TabDev *Tp, const TabDev &T,
                 price_consider(T, acc, c1, nc, label, bsz);
             }
         }
-        price_finish(T, s, acc, &found, &neg);
+        price_finish_rx(T, s, acc, &found, &neg);
     }
     if (tid == 0) ts[2] = clock64();
     if (found == 0 && nfull != INT_MAX) {  // nothing in the leading batches: price the whole row
@@ -521,7 +520,7 @@ __device__ __forceinline__ void cta_selector_decide(TabDev *Tp, const TabDev &T,
                 price_consider(T, acc, c, nc, label, bsz);
             }
         }
-        price_finish(T, s, acc, &found, &neg);
+        price_finish_rx(T, s, acc, &found, &neg);
     }
     if (tid == 0) {
         if (log_n < T.plog_cap) T.plog[log_n] = make_int4(rnext | (1 << 30), cn, leaving, entering);
@@ -625,7 +624,7 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
                 if (e.v < quo) { e.v = quo; e.i = c; }
             }
         }
-        e = block_reduce_vi<false>(e, einit, s.red);
+        e = block_reduce_vi_rx<false>(e, einit, s.red);
         if (e.i == INT_MAX) {  // simplex.ts:73-76
             if (tid == 0) finish(ST_INFEASIBLE, 0, -1);
             return;
@@ -718,7 +717,7 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
                 }
             }
         }
-        e = block_reduce_vi<false>(e, einit, s.red);
+        e = block_reduce_vi_rx<false>(e, einit, s.red);
         if (e.i == INT_MAX) {  // simplex.ts:73-76
             if (tid == 0) finish(ST_INFEASIBLE, 0, -1);
             return;
@@ -770,7 +769,7 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
                     price_consider(T, acc, c, nc, label, bsz);
                 }
             }
-            price_finish(T, s, acc, &cn, &isneg);
+            price_finish_rx(T, s, acc, &cn, &isneg);
         }
         if (cn == 0) {  // optimal (simplex.ts:265-269)
             if (tid == 0) finish(ST_OPTIMAL, 2, -1);
@@ -805,7 +804,7 @@ __device__ __noinline__ void cta_selector_decide_full(TabDev *Tp, const TabDev &
                 if (quo > prec && m.v > quo) { m.v = quo; m.i = r; }
             }
         }
-        block_reduce_ratio(dmin, m, cnt, s.red);
+        { int okd = 1; block_reduce_ratio_rx(dmin, m, cnt, okd, s.red); }
         if (dmin != INT_MAX) rnext = dmin;
         else if (m.i != INT_MAX) rnext = m.i;
         else {  // unbounded (simplex.ts:298-303)
@@ -948,7 +947,6 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     // plain (L1-cached) loads: 2368 warps read this one line, L1 serves all but the first per SM
     const int4 ra = rp[0], rb = rp[1], rc = rp[2], rd = rp[3], re = rp[4];
     const double q = rec->q;
-    const int gate = rec->pad1;  // experiment: hold the streaming warps until the partial is published
     if (tid == 0) T = *Tp;
     const int status = ra.x, phase = ra.y, has_pivot = ra.z, rstar = ra.w;
     const int cstar = rb.x, flush = rb.z, launch = rb.w;
@@ -1014,13 +1012,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                 const double rhs = new_entry(la_rhs, is_prow, la_coef, f_0, false, q);
                 VI m = {INFINITY, INT_MAX};
                 if (lane < nr && r0 + lane != 0 && rhs < -T.prec) { m.v = rhs; m.i = lane; }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    VI y;
-                    y.v = __shfl_xor_sync(0xffffffffu, m.v, o);
-                    y.i = __shfl_xor_sync(0xffffffffu, m.i, o);
-                    if (better<true>(y, m)) m = y;
-                }
+                m = warp_reduce_vi<true>(m);
                 if (lane == 0) {
                     mbar_wait(&bar, 0);  // a published partial also promises: this CTA is done reading prow
                     part_publish(T.part + b, m.v, m.i == INT_MAX ? 255 : m.i, 255, 0, (unsigned int)(launch + 1));
@@ -1051,15 +1043,9 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                         }
                     }
                 }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    VI y;
-                    y.v = __shfl_xor_sync(0xffffffffu, m.v, o);
-                    y.i = __shfl_xor_sync(0xffffffffu, m.i, o);
-                    if (better<true>(y, m)) m = y;
-                    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                }
+                m = warp_reduce_vi<true>(m);
+                dmin = __reduce_min_sync(0xffffffffu, dmin);
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
                 if (lane == 0) {
                     mbar_wait(&bar, 0);  // a published partial also promises: this CTA is done reading prow
                     part_publish(T.part + b, m.v, m.i == INT_MAX ? 255 : m.i, dmin == INT_MAX ? 255 : dmin, cnt,
@@ -1068,7 +1054,6 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
                 }
             }
         }
-        if (gate && la_warp) __syncwarp();
         mbar_wait(&bar, 0);
         if (!prow_norm) {
             for (int c = tid; c < T.stride; c += NT) {  // normalise (simplex.ts:352-364, 380-382)
