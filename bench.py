@@ -266,7 +266,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
                          # `ncu --set full` capture (profiles/r01_k_pivot_step_ncu.md, 2001x2001 only)
-                         "traffic": 32386304 + 383488 if args.size == 2000 else None,
+                         "traffic": 32382720 + 159488 if args.size == 2000 else None,
                          "peak_source": peak_src, "kernel": "k_pivot_step<256,2,4,prefetch> (ping-pong)",
                          "bytes_per_launch": bpp, "avg_launch_us": per_launch_us,
                          "note": "achieved = algorithmic bytes (SURVEY 8d: 16HW+8W+16H+8(H+W)) x pivots / event-timed "

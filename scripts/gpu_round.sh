@@ -21,6 +21,15 @@ if [ "${SKIP_BENCH:-0}" != "1" ]; then
     echo "bench exit $?"; cat gpurun_out/bench_e$eng.json; tail -n 5 gpurun_out/bench_e$eng.err
   done
 fi
+if [ "${SKIP_BENCH:-0}" != "1" ]; then
+  echo "== bench --impl reference (CPU arm: oracle port on the box's host cores)"
+  timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+  echo "reference exit $?"; cat gpurun_out/bench_reference.json
+fi
+if [ "${SKIP_MIP:-0}" != "1" ]; then
+  echo "== mip_bench (1 GPU)"
+  SPEC=${SPEC:-16,64} REPS=3 timeout 400 python scripts/mip_bench.py > gpurun_out/mip_bench.log 2>&1; echo "mip exit $?"; cut -c1-400 gpurun_out/mip_bench.log
+fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 400 --csv --log-file gpurun_out/launches.csv \
