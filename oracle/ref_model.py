@@ -568,7 +568,10 @@ class OracleTableau:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().orc_destroy(self.h)
+            try:
+                lib().orc_destroy(self.h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
             self.h = None
 
     def set_pivot_limit(self, n):
