@@ -95,3 +95,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle/", "").lower() or f in (), (f, "mentions oracle")
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof/offsetof of every struct in include/jslp_b200.h, as gcc sees them, equal the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+    from jslpsolver_b200 import _lib
+    structs = {"jslp_lp_status": _lib.LpStatus, "jslp_cut": _lib.Cut, "jslp_bnb_opts": _lib.BnbOpts,
+               "jslp_bnb_status": _lib.BnbStatus}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{os.path.join(ROOT, "include", "jslp_b200.h")}"',
+             "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
