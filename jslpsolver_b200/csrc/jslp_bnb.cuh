@@ -196,12 +196,9 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
     CK(cudaStreamSynchronize(s));  // inputs and outputs are mapped host memory: nothing to copy
     long long slowest = 0;
     bool need_full = false;
+    static const bool dbg = getenv("JSLP_DEBUG") != nullptr;  // per-node timeline on stderr (scripts/node_timeline.py)
     for (int i = 0; i < n; i++) {
-        if (rb.h_out[i].r.t_ns > slowest) {
-            static const bool dbg = getenv("JSLP_DEBUG") != nullptr;
-            if (dbg && i == n - 1) {}
-        }
-        if (getenv("JSLP_DEBUG")) {
+        if (dbg) {
             const NodeResult &q = rb.h_out[i].r;
             fprintf(stderr, "node r%d n%d i%d cuts %d piv %d+%d: off %lld restore %lld cuts %lld pivots %lld mip %lld end %lld cy %lld %lld %lld %lld %lld %lld\n",
                     (int)ctx->launches, n, i, (int)nodes[i]->cuts.size(), q.p1, q.p2, q.tl[0], q.tl[1], q.tl[2], q.tl[3], q.tl[4], q.t_ns, q.cy[0], q.cy[1], q.cy[2], q.cy[3], q.cy[4], q.cy[5]);
