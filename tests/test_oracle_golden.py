@@ -80,3 +80,54 @@ def test_cut_rows_known_answers():
     assert X[6].tolist() == [7.0, 0.0, 1.0]
     vrow2, _ = t.maps()
     assert vrow2.tolist() == [-1, 2, 3, 4, 5, 6, 7]
+
+
+def _mip_tableau(rhs, basic_vars, integers, precision=1e-9):
+    """Tableau whose row r >= 1 holds variable basic_vars[r-1] at value rhs[r-1] (RHS = column 0, as in the
+    reference's real tableau; its unit tests put it in column 2 of a mock)."""
+    H = len(rhs) + 1
+    M = np.zeros((H, 3))
+    M[1:, 0] = rhs
+    vrow = np.array([-1] + list(basic_vars), dtype=np.int32)
+    vcol = np.array([-1, 100, 101], dtype=np.int32)
+    return ref_model.OracleTableau(M, vrow, vcol, precision=precision, integers=list(integers))
+
+
+def test_is_integral_known_answers():
+    """The cases of the reference's mip-utils.test.ts:173-300 (isIntegral, mip-utils.ts:43-61)."""
+    assert _mip_tableau([5.0, 3.0], [1, 2], [1, 2]).is_integral() is True
+    assert _mip_tableau([5.0, 3.7], [1, 2], [1, 2]).is_integral() is False
+    assert _mip_tableau([5.5], [1], []).is_integral() is True                 # no integer variables
+    assert _mip_tableau([5.0], [1], [1, 2]).is_integral() is True             # variable 2 is not basic
+    assert _mip_tableau([4.9999999], [1], [1], precision=1e-6).is_integral() is True
+
+
+def test_most_fractional_known_answers():
+    """The cases of mip-utils.test.ts:431-565 (getMostFractionalVar, mip-utils.ts:100-126): largest distance
+    to the nearest integer, the first integer variable wins ties, non-basic variables are skipped."""
+    assert _mip_tableau([5.3, 3.7], [1, 2], [1, 2]).most_fractional() == (1, 5.3)   # both 0.3 away: first wins
+    assert _mip_tableau([5.1, 3.5], [1, 2], [1, 2]).most_fractional() == (2, 3.5)
+    assert _mip_tableau([5.3], [1], [1, 2]).most_fractional()[0] == 1               # variable 2 not basic
+    i, v = _mip_tableau([5.0], [1], [1]).most_fractional()                          # nothing fractional
+    assert i < 0 and v == 0.0
+    i, _ = _mip_tableau([5.5], [1], []).most_fractional()                           # no integer variables
+    assert i < 0
+
+
+def test_solver_options_known_answers():
+    """Known answers of the reference's solver.options.test.ts:68-136 that run through the default
+    branch-and-cut service (timeout removed: it is wall-clock)."""
+    r = ref_model.simplify(ref_model.solve_full({
+        "optimize": "profit", "opType": "max", "constraints": {"capacity": {"max": 10}},
+        "variables": {"x": {"profit": 5, "capacity": 2}}, "ints": {"x": 1}}))
+    assert r["feasible"] is True and r["x"] == 5
+    r = ref_model.simplify(ref_model.solve_full({
+        "optimize": "profit", "opType": "max", "constraints": {"budget": {"max": 100}},
+        "variables": {"a": {"profit": 10, "budget": 10}, "b": {"profit": 15, "budget": 15}, "c": {"profit": 20, "budget": 20}},
+        "ints": {"a": 1, "b": 1, "c": 1}, "tolerance": 0.1}))
+    assert r["feasible"] is True and r["result"] >= 90
+    r = ref_model.simplify(ref_model.solve_full({
+        "optimize": "profit", "opType": "max", "constraints": {"budget": {"max": 100}},
+        "variables": {"a": {"profit": 10, "budget": 10}, "b": {"profit": 8, "budget": 10}},
+        "ints": {"a": 1, "b": 1}, "tolerance": 0}))
+    assert r["feasible"] is True and r["result"] == 100
