@@ -1,18 +1,35 @@
 // jslpsolver_b200/csrc/jslp_step.cuh -- the fused pivot step (included by jslp_kernels.cuh).
 //
-// One launch == one simplex iteration on a tableau that lives in HBM / L2:
-//   head   TMA (cp.async.bulk + mbarrier) stages the raw pivot row into shared memory; every CTA
-//          normalises it there (simplex.ts:352-364, lazy flush 380-382)
-//   body   each CTA streams its block of rows with 128-bit loads/stores:
-//          M[r][c] = M[r][c] - coef_r * prow[c]   (two roundings, simplex.ts:379), pivot column
-//          entry -coef_r / q (385), pivot row rewrite, optional-objective rows (393-412)
-//   look-ahead (phase 2)  the entering column of the NEXT pivot was priced one step ahead (it only
-//          needs the updated cost row, which is known as soon as this pivot is chosen), so each CTA
-//          runs the ratio test (271-296) on its own freshly written rows and publishes a 40-byte
-//          partial; it also stages the next pivot column
-//   tail   the last CTA (atomic ticket) reduces the partials to the leaving row, stages the pivot
-//          (raw row copy, label swap, log) and prices the pivot after that one.  When look-ahead
-//          does not apply (phase 1, optional objectives, bootstrap) it runs the generic selection.
+// One launch == one simplex iteration on a tableau that lives in HBM / L2.  Two instantiations of
+// k_pivot_step<threads, occupancy, rows per pass, prefetch, PP>:
+//
+// PP = true, the ping-pong step (every step of a solve without optional objectives and with at most 32
+// rows per row CTA).  The tableau is read from T.M and written to T.M2, then the two pointers are swapped
+// in the device descriptor, so old values stay readable for the whole launch and the NEXT pivot is chosen
+// beside the streaming, not after it.  Grid = G row CTAs + 2 selector CTAs.
+//   head   TMA (cp.async.bulk + mbarrier) pulls the pivot row -- staged already normalised by the previous
+//          launch (simplex.ts:352-364, lazy flush 380-382) -- into shared memory; it is issued before
+//          anything else because it needs only kernel parameters.  The pivot record (one 128-byte line) and
+//          the descriptor are requested together: the head is one L2 round trip deep.
+//   row CTA  last warp = look-ahead of the next pivot on this CTA's rows, computed from OLD values with
+//          new_entry(): ratio-test partial (phase 2, simplex.ts:271-296) or most negative right-hand side
+//          (phase 1, 38-54), published as one self-validating 16-byte message.  All warps then stream the
+//          row block: M2[r][c] = M[r][c] - coef_r * prow[c] (two roundings, simplex.ts:379), pivot column
+//          entry -coef_r / q (385), pivot row rewrite.
+//   selector S1  polls the G messages and reduces them (redux.sync on order-preserving keys) to the next
+//          leaving row; phase 2: derives that row and the cost row from the old tableau, prices the pivot
+//          AFTER next (140-219), writes the record, swaps labels, flips the descriptor
+//          (cta_selector_decide).  Phase 1, and phase-2 pivots without a priced successor: also picks the
+//          entering column (56-76) or runs pricing + ratio test on derived values, and stages the next
+//          pivot row itself (cta_selector_decide_full).
+//   selector S2  (phase 2) stages the normalised next pivot row into the prow side buffer.
+//
+// PP = false, the in-place step (two-kernel engine, optional objectives 393-412, very tall tableaux):
+// rank-1 update in place; with do_select the last CTA to finish (atomic ticket) reduces look-ahead partials
+// (cta_tail_lookahead) or runs the generic selection (cta_select<true>).
+//
+// Code layout matters as much as instruction count here: hot paths are inlined and
+// contiguous, rarely taken ones are __noinline__.
 #pragma once
 // (included inside namespace jslp)
 
