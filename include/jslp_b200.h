@@ -73,8 +73,8 @@ int jslp_tab_upload(jslp_tab *tab, const double *matrix, const int32_t *var_inde
 
 /* Solver options that the reference keeps on Model / Tableau. */
 enum {
-    JSLP_OPT_ENGINE = 1,       /* 0 = auto, 1 = two-kernel (select + update), 2 = fused step,
-                                  3 = persistent fused, 4 = single-CTA resident            */
+    JSLP_OPT_ENGINE = 1,       /* 0 = auto (resident when H*W <= 16384, else fused), 1 = two-kernel
+                                  (select + update), 2 = fused step, 4 = single-CTA resident    */
     JSLP_OPT_BATCH = 2,        /* pivots enqueued per host poll (default 256)              */
     JSLP_OPT_PIVOT_LOG_CAP = 3, /* keep a host-side (row,col,leaving,entering) log, 0 = off */
     /* tuning / diagnostics of the fused pivot step (no effect on results) */
@@ -83,7 +83,7 @@ enum {
     JSLP_OPT_LOOKAHEAD = 6,    /* 1 (default) = look-ahead ratio test, 0 = generic serial tail    */
     JSLP_OPT_TIMELINE = 7,     /* record a per-CTA timeline for the first N launches of a solve   */
     JSLP_OPT_PDL = 8,          /* 1 = chain the fused steps with programmatic dependent launch    */
-    JSLP_OPT_PINGPONG = 9      /* 1 (default) = ping-pong tableau + selector CTA, 0 = in-place    */
+    JSLP_OPT_PINGPONG = 9      /* 1 (default) = ping-pong tableau + two selector CTAs, 0 = in place */
 };
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
 /* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */
