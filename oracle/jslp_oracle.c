@@ -159,8 +159,14 @@ void orc_upload(orc_tab *t, const double *matrix, const int *vrow, const int *vc
     memcpy(t->vrow, vrow, sizeof(int) * t->H);
     memcpy(t->vcol, vcol, sizeof(int) * t->W);
     for (int i = 0; i < t->mapCap; i++) { t->rowOf[i] = -1; t->colOf[i] = -1; }
-    for (int r = 1; r < t->H; r++) t->rowOf[vrow[r]] = r;
-    for (int c = 1; c < t->W; c++) t->colOf[vcol[c]] = c;
+    for (int r = 1; r < t->H; r++) {
+        if (vrow[r] < 0 || vrow[r] >= t->mapCap) { fprintf(stderr, "orc_upload: row label %d out of range\n", vrow[r]); abort(); }
+        t->rowOf[vrow[r]] = r;
+    }
+    for (int c = 1; c < t->W; c++) {
+        if (vcol[c] < 0 || vcol[c] >= t->mapCap) { fprintf(stderr, "orc_upload: column label %d out of range\n", vcol[c]); abort(); }
+        t->colOf[vcol[c]] = c;
+    }
 }
 
 void orc_set_unrestricted(orc_tab *t, const unsigned char *flags, int n) {

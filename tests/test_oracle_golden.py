@@ -89,7 +89,10 @@ def _mip_tableau(rhs, basic_vars, integers, precision=1e-9):
     M = np.zeros((H, 3))
     M[1:, 0] = rhs
     vrow = np.array([-1] + list(basic_vars), dtype=np.int32)
-    vcol = np.array([-1, 100, 101], dtype=np.int32)
+    n_vars = 3 + H - 2  # the oracle sizes its inverse maps by width + height - 2, like the reference
+    free = [v for v in range(n_vars) if v not in basic_vars]
+    assert len(free) == 2
+    vcol = np.array([-1] + free, dtype=np.int32)
     return ref_model.OracleTableau(M, vrow, vcol, precision=precision, integers=list(integers))
 
 
