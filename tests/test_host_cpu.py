@@ -120,3 +120,15 @@ def test_ctypes_structs_match_the_header(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_frontier_heap_follows_the_reference_min_heap(tmp_path):
+    """tests/cpp/frontier_test.cpp: the product's frontier (jslp_frontier.h, host-only) replays the ordering
+    scenarios of the reference's min-heap.test.ts (best-first, LIFO on ties) and the all-gather record round trip."""
+    import subprocess
+    exe = tmp_path / "frontier_test"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "jslpsolver_b200", "csrc"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "cpp", "frontier_test.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "FRONTIER OK" in out.stdout, out.stdout + out.stderr
