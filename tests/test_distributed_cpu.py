@@ -56,7 +56,7 @@ def test_all_gather_hook_world2_gloo(tmp_path):
 
 def test_wire_record_layout_matches_header():
     """The all-gathered record is 16 doubles (128 bytes) per node: keep doc and code in sync."""
-    src = open(os.path.join(ROOT, "jslpsolver_b200", "csrc", "jslp_bnb.cuh")).read()
+    src = open(os.path.join(ROOT, "jslpsolver_b200", "csrc", "jslp_frontier.h")).read()
     assert "WIRE_DOUBLES = 16" in src
 
 
