@@ -132,3 +132,14 @@ def test_frontier_heap_follows_the_reference_min_heap(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "frontier_test.cpp")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "FRONTIER OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_cycle_detectors_follow_the_reference_scan(tmp_path):
+    """tests/cpp/cycles_test.cpp: the product's two host-side detectors (jslp_cycles.h) report exactly what a literal
+    restatement of checkForCycles (simplex.ts:415-440) reports, push by push, on 4000 random pivot histories."""
+    import subprocess
+    exe = tmp_path / "cycles_test"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "jslpsolver_b200", "csrc"),
+                    "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "cycles_test.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "CYCLES OK" in out.stdout, out.stdout + out.stderr
