@@ -10,6 +10,7 @@
 #include "../../include/jslp_b200.h"
 #include "jslp_kernels.cuh"
 #include "jslp_node_kernel.cuh"
+#include "jslp_hostmath.h"
 
 #include <algorithm>
 #include <cmath>
@@ -568,16 +569,9 @@ static int get_graph(jslp_tab *t, int eidx, int kind, cudaGraphExec_t *out) {
     return JSLP_OK;
 }
 
-static double js_round_h(double x) {
-    if (!(x == x) || std::isinf(x)) return x;
-    const double f = std::floor(x);
-    return (x - f >= 0.5) ? f + 1.0 : f;
-}
-
 // tableau.ts:420-430
 static void set_evaluation(jslp_tab *t, double raw) {
-    const double roundingCoeff = js_round_h(1 / t->precision);
-    const double rounded = js_round_h((2.220446049250313e-16 + raw) * roundingCoeff) / roundingCoeff;
+    const double rounded = jslp_round_evaluation(raw, t->precision);
     t->evaluation = rounded;
     if (t->simplexIters == 0) t->bestPossibleEval = rounded;
 }

@@ -163,8 +163,7 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
         ev.bounded = r.status != ST_UNBOUNDED;
         ev.feasible = r.status == ST_OPTIMAL || r.status == ST_UNBOUNDED;
         if (r.status == ST_OPTIMAL) {
-            const double roundingCoeff = js_round_h(1 / t->precision);
-            ev.evaluation = js_round_h((2.220446049250313e-16 + r.eval_raw) * roundingCoeff) / roundingCoeff;
+            ev.evaluation = jslp_round_evaluation(r.eval_raw, t->precision);
         } else if (r.status == ST_UNBOUNDED) {
             ev.evaluation = -INFINITY;
         } else {

@@ -143,3 +143,32 @@ def test_cycle_detectors_follow_the_reference_scan(tmp_path):
                     "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "cycles_test.cpp")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "CYCLES OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_host_rounding_matches_the_oracle(tmp_path):
+    """tests/cpp/hostmath_test.cpp: the product's Math.round / setEvaluation (jslp_hostmath.h) against the oracle's
+    restatement (tableau.ts:420-430), bit for bit, on tie cases and random magnitudes."""
+    import struct
+    import subprocess
+    from oracle import ref_model
+    exe = tmp_path / "hostmath_test"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "jslpsolver_b200", "csrc"),
+                    "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "hostmath_test.cpp")], check=True)
+    rng = np.random.default_rng(7)
+    xs = [0.0, -0.0, 0.5, -0.5, 1.5, 2.5, -2.5, 0.49999999999999994, 1e15 + 0.5, -1e15 - 0.5, 681907.6430000001,
+          25432.999999995, -523.612072085, 1e-9, -1e-9, 5e-9, -5e-9, float("inf"), float("-inf")]
+    xs += list(rng.normal(0, 1, 300) * 10.0 ** rng.integers(-9, 9, 300))
+    xs += [float(k) + 0.5 * 1e-8 * s for k in range(-3, 4) for s in (-1, 1)]  # ties at the 1e-8 grid
+    cases = [(x, p) for x in xs for p in (1e-8, 1e-9, 1e-6)]
+    bits = lambda v: struct.unpack("<Q", struct.pack("<d", v))[0]
+    stdin = "".join(f"{bits(x):x} {bits(p):x}\n" for x, p in cases)
+    out = subprocess.run([str(exe)], input=stdin, capture_output=True, text=True, check=True).stdout.split()
+    assert len(out) == 2 * len(cases)
+    for k, (x, p) in enumerate(cases):
+        coeff = ref_model.js_round(1 / p)
+        want_r = ref_model.js_round(x)
+        want_e = ref_model.js_round((2.220446049250313e-16 + x) * coeff) / coeff
+        # the sign of a zero result is not compared: JS gives -0 on [-0.5, 0], observable nowhere in the reference
+        same = lambda got, want: got == bits(float(want)) or (want == 0 and got in (0, 1 << 63))
+        assert same(int(out[2 * k], 16), want_r), (x, "round")
+        assert same(int(out[2 * k + 1], 16), want_e), (x, p, "evaluation")
