@@ -322,7 +322,7 @@ __device__ __forceinline__ double priced_cost(double cost, double v, double coef
         const double f = nz16(v) ? ddiv(v, q) : 0.0;
         return nz16(f) ? __dsub_rn(cost, __dmul_rn(coef0, f)) : cost;
     }
-    return (coef0 != 0.0 && is_pc) ? 0.0 : cost;
+    return cost;  // |coef0| <= 1e-16: the cost row is untouched (simplex.ts:371; :389-391 is dead code)
 }
 
 struct SelSmem {

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
         const double q = piv.q;
         // ---- D (CTA): both division passes at once: the lower half of the CTA normalises the pivot row
         // (simplex.ts:352-364 + lazy flush 380-382), the upper half rewrites the pivot column
-        // (simplex.ts:372-374,386-388) after staging its old entries for the row updates.
+        // (simplex.ts:371-374,386) after staging its old entries for the row updates.
         if (tid < NT / 2) {
             const double *praw = Ms + (size_t)slot[prs] * Ws;
 #pragma unroll 1
@@ -350,8 +350,7 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node_batch(const TabDev *Tp, c
                 double *e = Ms + (size_t)slot[r] * Ws + pcs;
                 const double coef = *e;
                 pcol[r] = coef;
-                if (nz16(coef)) *e = ddiv_z(-coef, q);
-                else if (coef != 0.0) *e = 0.0;
+                if (nz16(coef)) *e = ddiv_z(-coef, q);  // else untouched (simplex.ts:371; :389-391 is dead code)
             }
         }
         NODE_CY(3);

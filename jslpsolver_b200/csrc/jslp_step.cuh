@@ -84,7 +84,8 @@ __device__ __noinline__ void update_rows(const TabDev &T, const double *frow, in
             coef[j] = valid ? pcol[r] : 0.0;
             act[j] = valid && nz16(coef[j]);
             any |= act[j];
-            if (valid && !act[j] && coef[j] != 0.0 && tid == 0) Mb[r * stride + cstar] = 0.0;  // simplex.ts:386-388
+            // simplex.ts:389-391 is dead code in the reference (same predicate as :371): a pivot-column
+            // entry with |x| <= 1e-16 is left untouched.
         }
         double *const base = Mb + (size_t)rb * stride;
         if (any && !PF) {
@@ -164,7 +165,7 @@ __device__ __forceinline__ double new_entry(double old, bool is_prow, double coe
         if (is_pc) return ddiv(-coef, q);
         return nz16(f) ? __dsub_rn(old, __dmul_rn(coef, f)) : old;
     }
-    return (coef != 0.0 && is_pc) ? 0.0 : old;
+    return old;  // |coef| <= 1e-16: the row is untouched, its pivot-column entry included (simplex.ts:371,389-391 dead)
 }
 
 // ---- look-ahead: ratio-test partial of this CTA's rows against the next entering column ---------
@@ -307,10 +308,7 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
                 double2 nv;
                 if (isp[j]) nv = f;                                                   // normalised pivot row
                 else if (act[j]) nv = upd2(old[j], f, z0, z1, coef[j], pc, codd, q);  // rank-1 update
-                else {                                                                // untouched row
-                    nv = old[j];
-                    if (pc && coef[j] != 0.0) { if (codd) nv.y = 0.0; else nv.x = 0.0; }  // simplex.ts:386-388
-                }
+                else nv = old[j];  // untouched row, tiny pivot-column entry included (simplex.ts:371; :389-391 is dead)
                 st_v2(db + j * stride + 2 * c2, nv);
             }
         };

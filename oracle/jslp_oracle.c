@@ -266,9 +266,12 @@ void orc_pivot(orc_tab *t, int pr, int pc) {
                 }
             }
             row[pc] = -coefficient / quotient;
-        } else if (coefficient != 0) {
-            row[pc] = 0;
         }
+        /* simplex.ts:389-391: the reference's `else if (coefficient !== 0) matrix[...] = 0` sits INSIDE
+         * `if (!(pivotColVal >= -1e-16 && pivotColVal <= 1e-16))` (:371) and tests the same value with the
+         * same predicate (:374), so it is dead code: a pivot-column entry with |x| <= 1e-16 (tiny non-zero
+         * included) is left untouched.  Round 1 flattened the two ifs and made the branch live, which
+         * changed low-order bits and, through them, the B&B path of StockCuttingProblem / Vendor Selection. */
     }
 
     for (int o = 0; o < t->nOpt; o++) {

@@ -11,19 +11,12 @@ from oracle import ref_model
 
 BUNDLE = load_bundle()
 
-# Objective pinned, variable assignment unconfirmed (alternative optima): the
-# reference's own vitest run skips Vendor Selection (solver.integration.test.ts:154).
-ASSIGNMENT_UNCONFIRMED = {"StockCuttingProblem.json", "Vendor Selection.json"}
-
 
 @pytest.mark.parametrize("fx", BUNDLE["fixtures"] + BUNDLE["readme"], ids=lambda f: f["file"])
 def test_fixture_expects(fx):
     res = ref_model.Solve(strip_timeouts(fx["model"]), fast_cycles=True)
     bad = compare_solutions(res, fx["expects"])
-    if fx["file"] in ASSIGNMENT_UNCONFIRMED:
-        assert not [b for b in bad if b.startswith(("result", "feasible"))], bad
-    else:
-        assert not bad, bad
+    assert not bad, bad     # every fixture on every listed key, no exceptions
 
 
 def test_readme_berlin_pivot_sequence():
