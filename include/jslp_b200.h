@@ -83,7 +83,11 @@ enum {
     JSLP_OPT_LOOKAHEAD = 6,    /* 1 (default) = look-ahead ratio test, 0 = generic serial tail    */
     JSLP_OPT_TIMELINE = 7,     /* record a per-CTA timeline for the first N launches of a solve   */
     JSLP_OPT_PDL = 8,          /* 1 = chain the fused steps with programmatic dependent launch    */
-    JSLP_OPT_PINGPONG = 9      /* 1 (default) = ping-pong tableau + two selector CTAs, 0 = in place */
+    JSLP_OPT_PINGPONG = 9,     /* 1 (default) = ping-pong tableau + two selector CTAs, 0 = in place */
+    /* branch-and-cut nodes too large for shared memory (no effect on results) */
+    JSLP_OPT_NODE_SLOTS = 10,  /* node LPs in flight side by side in HBM: -1 = auto (default), 0 = one at a
+                                  time (the reference's literal applyCuts sequence), n = at most n slots */
+    JSLP_OPT_SLOT_STEPS = 11   /* pivots per slot between host polls of the slot batch (default 32)   */
 };
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
 /* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */

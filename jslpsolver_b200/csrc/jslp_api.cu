@@ -10,6 +10,7 @@
 #include "../../include/jslp_b200.h"
 #include "jslp_kernels.cuh"
 #include "jslp_node_kernel.cuh"
+#include "jslp_slots.cuh"
 #include "jslp_hostmath.h"
 
 #include <algorithm>
@@ -40,6 +41,7 @@ struct jslp_ctx {
     bool owns_stream = false;
     int num_sms = 148;
     int max_smem_optin = 48 * 1024;
+    int64_t l2_bytes = 64 << 20;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -150,6 +152,9 @@ struct jslp_tab {
     Snapshot snaps[2];  // one restart point per in-flight batch
     std::vector<NodeLogEntry> node_log;
     ResidentBufs rbufs;
+    NodeSlots slots;        // K3: HBM-resident node batch (jslp_slots.cuh)
+    int node_slots = -1;    // JSLP_OPT_NODE_SLOTS: -1 = auto, 0 = off (one node at a time), n = at most n slots
+    int slot_steps = 32;    // pivots per slot per host poll
     long long node_kernel_ns = 0;  // sum over rounds of the slowest node CTA (reporting)
 };
 
@@ -171,6 +176,7 @@ extern "C" int jslp_ctx_create(int device, void *stream, jslp_ctx **out) {
     CK(cudaGetDeviceProperties(&p, device));
     c->num_sms = p.multiProcessorCount;
     c->max_smem_optin = (int)p.sharedMemPerBlockOptin;
+    c->l2_bytes = p.l2CacheSize > 0 ? (int64_t)p.l2CacheSize : c->l2_bytes;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -314,6 +320,7 @@ extern "C" void jslp_tab_destroy(jslp_tab *t) {
     if (t->ev_slot[0]) cudaEventDestroy(t->ev_slot[0]);
     if (t->ev_slot[1]) cudaEventDestroy(t->ev_slot[1]);
     t->rbufs.release();
+    t->slots.release();
     delete t;
 }
 
@@ -401,6 +408,14 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
             return JSLP_OK;
         case JSLP_OPT_PDL:
             t->pdl = value != 0;  // programmatic-dependent-launch edges inside the graph (measured: no gain)
+            return JSLP_OK;
+        case JSLP_OPT_NODE_SLOTS:
+            if (value < -1 || value > 64) return fail(JSLP_E_INVALID, "node slots must be -1..64");
+            t->node_slots = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_SLOT_STEPS:
+            if (value < 1 || value > 1024) return fail(JSLP_E_INVALID, "slot steps must be 1..1024");
+            t->slot_steps = (int)value;
             return JSLP_OK;
         case JSLP_OPT_TIMELINE:
             if (value < 0 || value > 4096) return fail(JSLP_E_INVALID, "timeline launches must be 0..4096");

@@ -66,6 +66,206 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
     return JSLP_OK;
 }
 
+// ---- K3: HBM-resident node batch (jslp_slots.cuh) ---------------------------------------------
+// Largest number of slots for which every slot still runs the ping-pong step (at most 32 rows per row CTA,
+// all B * (G + 2) CTAs co-resident), capped by the option and by what keeps the tableau pairs in L2.
+static int slots_for(const jslp_tab *t, int rowcap, int want) {
+    if (t->node_slots == 0 || want < 2) return 0;
+    if (!(t->pingpong && t->lookahead && t->nOpt == 0) || t->engine == 1) return 0;
+    const StepVariant &sv = step_variant(t);
+    const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
+    const int C = t->ctx->num_sms * per_sm;
+    int geom = 0;
+    for (int b = 1; b <= 64; b++) {
+        const int G = C / b - 2;
+        if (G < 1 || rowcap / G + 1 > 32) break;
+        geom = b;
+    }
+    int cap = geom;
+    if (t->node_slots > 0) cap = std::min(cap, t->node_slots);
+    else {  // auto: keep the ping-pong pairs of all slots inside L2 (each pivot re-reads what the last one wrote)
+        const double pair_bytes = 16.0 * (double)rowcap * t->stride;
+        const int l2 = (int)std::floor(0.85 * (double)t->ctx->l2_bytes / pair_bytes);
+        cap = std::min(cap, std::max(2, l2));
+    }
+    return std::min(cap, want) >= 2 ? std::min(cap, want) : 0;
+}
+
+static int ensure_slots(jslp_tab *t, int B, int need_rowcap) {
+    NodeSlots &ns = t->slots;
+    jslp_ctx *ctx = t->ctx;
+    cudaStream_t s = ctx->stream;
+    const StepVariant &sv = step_variant(t);
+    const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
+    const int G = ctx->num_sms * per_sm / B - 2;
+    const int S = t->slot_steps;
+    const int stride = t->stride;
+    if (ns.B != B || ns.rowcap < need_rowcap) {
+        CK(cudaStreamSynchronize(s));
+        const int rowcap = std::max(need_rowcap + 32, std::max(ns.rowcap, t->saved.H + 64));
+        ns.release();
+        ns.B = B; ns.rowcap = rowcap;
+        ns.plog_cap = 1024;
+        const size_t tab = (size_t)rowcap * stride;
+        CK(cudaMalloc(&ns.d_T, sizeof(TabDev) * B));
+        CK(cudaMalloc(&ns.d_rec, sizeof(Rec) * B));
+        CK(cudaMalloc(&ns.M, sizeof(double) * tab * B));
+        CK(cudaMalloc(&ns.M2, sizeof(double) * tab * B));
+        CK(cudaMalloc(&ns.prow, sizeof(double) * (size_t)stride * B));
+        CK(cudaMalloc(&ns.crow, sizeof(double) * (size_t)stride * B));
+        CK(cudaMalloc(&ns.pcol, sizeof(double) * (size_t)rowcap * B));
+        CK(cudaMalloc(&ns.vrow, sizeof(int) * (size_t)rowcap * B));
+        CK(cudaMalloc(&ns.vcol, sizeof(int) * (size_t)t->W * B));
+        CK(cudaMalloc(&ns.part, sizeof(Part) * (size_t)(ctx->num_sms * 16) * B));
+        CK(cudaMalloc(&ns.plog, sizeof(int4) * (size_t)ns.plog_cap * B));
+        CK(cudaMallocHost(&ns.h_logs, sizeof(int4) * (size_t)ns.plog_cap * B));
+        CK(cudaMemsetAsync(ns.M, 0, sizeof(double) * tab * B, s));
+        CK(cudaMemsetAsync(ns.M2, 0, sizeof(double) * tab * B, s));
+        CK(cudaMemsetAsync(ns.prow, 0, sizeof(double) * (size_t)stride * B, s));
+        CK(cudaMemsetAsync(ns.pcol, 0, sizeof(double) * (size_t)rowcap * B, s));
+        CK(cudaMemsetAsync(ns.part, 0xff, sizeof(Part) * (size_t)(ctx->num_sms * 16) * B, s));
+        int rc;
+        if ((rc = ResidentBufs::mapped(&ns.h_ctl, &ns.dv_ctl, sizeof(SlotCtl) * B))) return rc;
+        if ((rc = ResidentBufs::mapped(&ns.h_out, &ns.dv_out, sizeof(SlotOut) * B))) return rc;
+        ns.cuts_cap = B * (rowcap - t->saved.H);
+        if ((rc = ResidentBufs::mapped(&ns.h_cuts, &ns.dv_cuts, sizeof(CutDev) * (size_t)std::max(1, ns.cuts_cap)))) return rc;
+        std::vector<TabDev> hd((size_t)B, t->hd);
+        std::vector<Rec> hr((size_t)B);
+        for (int b = 0; b < B; b++) {
+            TabDev &d = hd[b];
+            d.M = ns.M + tab * b; d.M2 = ns.M2 + tab * b;
+            d.prow = ns.prow + (size_t)stride * b; d.crow = ns.crow + (size_t)stride * b;
+            d.pcol = ns.pcol + (size_t)rowcap * b;
+            d.vrow = ns.vrow + (size_t)rowcap * b; d.vcol = ns.vcol + (size_t)t->W * b;
+            d.part = ns.part + (size_t)(ctx->num_sms * 16) * b;
+            d.plog = ns.plog + (size_t)ns.plog_cap * b; d.plog_cap = ns.plog_cap;
+            d.opt = nullptr; d.optcoef = nullptr; d.dbg = nullptr; d.dbg_cap = 0; d.dbg_grid = 0; d.nOpt = 0;
+            d.W = t->W; d.H = t->saved.H; d.stride = stride; d.rowcap = rowcap;
+            d.n_index = t->n_index; d.prec = t->precision;
+            memset(&hr[b], 0, sizeof(Rec));
+            hr[b].status = ST_P1_DONE;
+            ns.h_ctl[b] = SlotCtl{SLOT_IDLE, 0, 0, 0};
+        }
+        CK(cudaMemcpyAsync(ns.d_T, hd.data(), sizeof(TabDev) * B, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ns.d_rec, hr.data(), sizeof(Rec) * B, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        ns.key = -1;
+    }
+    // the graph bakes in the launch geometry and the snapshot it restores from
+    const int key = (int)((((size_t)t->saved.M >> 4) * 2654435761u) ^ (size_t)(t->variant * 131 + G * 7 + S * 1009 + t->saved.H * 31 +
+                          t->saved.lastElementIndex * 17 + B)) & 0x7fffffff;
+    if (ns.graph && ns.key == key && ns.G == G && ns.steps == S) return JSLP_OK;
+    if (ns.graph) { cudaGraphExecDestroy(ns.graph); ns.graph = nullptr; }
+    if (S + 2 > ns.plog_cap) return fail(JSLP_E_INVALID, "slot steps exceed the slot pivot-log capacity");
+    if (G + 2 > ctx->num_sms * 16) return fail(JSLP_E_INVALID, "slot grid exceeds the partial-message buffer");
+    const int smem = stride * 8;
+    CK(cudaFuncSetAttribute(sv.fn_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SlotBatchDev sb;
+    memset(&sb, 0, sizeof(sb));
+    sb.T = ns.d_T; sb.rec = ns.d_rec; sb.ctl = ns.dv_ctl; sb.cuts = ns.dv_cuts; sb.out = ns.dv_out;
+    sb.rootM = t->saved.M; sb.root_vrow = t->saved.vrow; sb.root_vcol = t->saved.vcol;
+    sb.H0 = t->saved.H; sb.first_index = t->saved.lastElementIndex; sb.part_n = G + 2; sb.lookahead = 1;
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    k_slot_begin<<<dim3(std::max(8, G + 2), B), 256, 0, s>>>(sb);
+    k_select<<<B, 512, 0, s>>>(ns.d_T, ns.d_rec, -1, -1);
+    for (int i = 0; i < S; i++)
+        sv.fn_pp<<<dim3(G + 2, B), sv.threads, smem, s>>>(ns.d_T, ns.d_rec, 2, ns.prow, stride);
+    k_slot_end<<<B, 256, 0, s>>>(sb);
+    cudaMemcpy2DAsync(ns.h_logs, sizeof(int4) * (size_t)(S + 2), ns.plog, sizeof(int4) * (size_t)ns.plog_cap,
+                      sizeof(int4) * (size_t)(S + 2), B, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("slot graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ns.graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(JSLP_E_CUDA, std::string("slot graph instantiate: ") + cudaGetErrorString(e));
+    ns.key = key; ns.G = G; ns.steps = S;
+    return JSLP_OK;
+}
+
+// Evaluates nodes[0..n) in B slots side by side.  Nodes whose pivot log shows a cycle are re-evaluated on the
+// single-tableau HBM path (exact stop-before-the-repeat semantics there).
+static int eval_nodes_slots(jslp_tab *t, jslp_bnb::Branch *const *nodes, int n, int B, int check_cycles) {
+    jslp_ctx *ctx = t->ctx;
+    cudaStream_t s = ctx->stream;
+    int maxc = 0;
+    for (int i = 0; i < n; i++) maxc = std::max(maxc, (int)nodes[i]->cuts.size());
+    int rc = ensure_slots(t, B, t->saved.H + maxc);
+    if (rc) return rc;
+    NodeSlots &ns = t->slots;
+    const int S = ns.steps;
+    static const bool dbg = getenv("JSLP_DEBUG") != nullptr;
+    std::vector<int> node_of((size_t)B, -1), redo;
+    std::vector<CycleHist> hist((size_t)2 * B);
+    int next = 0, done = 0;
+    while (done < n) {
+        int tot = 0;
+        for (int b = 0; b < B; b++) {
+            if (node_of[b] < 0 && next < n) {
+                const std::vector<jslp_cut> &cuts = nodes[next]->cuts;
+                if (tot + (int)cuts.size() > ns.cuts_cap) return fail(JSLP_E_CAPACITY, "slot cut buffer overflow");
+                ns.h_ctl[b] = SlotCtl{SLOT_LOAD, (int)cuts.size(), tot, 0};
+                for (const jslp_cut &c : cuts) {
+                    ns.h_cuts[tot].type = c.type; ns.h_cuts[tot].var_index = c.var_index; ns.h_cuts[tot].value = c.value;
+                    tot++;
+                }
+                node_of[b] = next++;
+                hist[2 * b] = CycleHist(); hist[2 * b + 1] = CycleHist();
+            } else {
+                ns.h_ctl[b].cmd = node_of[b] >= 0 ? SLOT_CONTINUE : SLOT_IDLE;
+            }
+        }
+        const auto t_g = std::chrono::steady_clock::now();
+        CK(cudaGraphLaunch(ns.graph, s));
+        ctx->launches += 3 + S;
+        CK(cudaStreamSynchronize(s));
+        if (dbg) {
+            int running = 0, loads = 0;
+            for (int b = 0; b < B; b++) { running += node_of[b] >= 0; loads += ns.h_ctl[b].cmd == SLOT_LOAD; }
+            fprintf(stderr, "slot graph: B %d G %d S %d running %d loads %d: %.0f us\n", B, ns.G, S, running, loads,
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_g).count());
+        }
+        for (int b = 0; b < B; b++) {
+            const int i = node_of[b];
+            if (i < 0) continue;
+            const Rec &r = ns.h_out[b].rec;
+            if (r.status == ST_ERROR) return fail(JSLP_E_CUDA, "slot batch: selector CTA timed out waiting for row CTAs");
+            if (r.log_n > S + 2) return fail(JSLP_E_CAPACITY, "slot pivot log overflow inside one batch");
+            bool hit = false;
+            if (check_cycles) {
+                const int4 *lg = ns.h_logs + (size_t)b * (S + 2);
+                int cs, cl;
+                for (int k = 0; k < r.log_n && !hit; k++) {
+                    CycleHist &h = hist[2 * b + (((lg[k].x >> 30) & 1) ? 1 : 0)];
+                    hit = h.push_and_check(((long long)lg[k].z << 32) | (unsigned int)lg[k].w, &cs, &cl);
+                }
+            }
+            if (hit) { redo.push_back(i); node_of[b] = -1; done++; continue; }
+            if (r.status == ST_RUNNING) continue;
+            jslp_bnb::NodeEval &ev = nodes[i]->ev;
+            ev.valid = true;
+            ev.pivots = r.p1 + r.p2;
+            ev.optimal = r.status == ST_OPTIMAL;
+            ev.bounded = r.status != ST_UNBOUNDED;
+            ev.feasible = r.status == ST_OPTIMAL || r.status == ST_UNBOUNDED;
+            ev.evaluation = r.status == ST_OPTIMAL ? jslp_round_evaluation(r.eval_raw, t->precision)
+                                                   : (r.status == ST_UNBOUNDED ? -INFINITY : 0.0);
+            const MipOut &mo = ns.h_out[b].mip;
+            ev.is_integral = ev.feasible ? mo.is_integral : 0;
+            ev.branch_var = ev.feasible ? mo.var_index : -1;
+            ev.branch_value = ev.feasible ? mo.value : 0.0;
+            if (dbg) fprintf(stderr, "slot node: slot %d cuts %d pivots %d+%d status %d\n", b, (int)nodes[i]->cuts.size(), r.p1, r.p2, r.status);
+            node_of[b] = -1;
+            done++;
+        }
+    }
+    for (int i : redo) {
+        rc = eval_node_streaming(t, *nodes[i], check_cycles, nodes[i]->ev);
+        if (rc) return rc;
+    }
+    return JSLP_OK;
+}
+
 static size_t node_smem_bytes(int Hcap, int W, int *Ws_out) {
     const int Ws = (W + 1) & ~1;  // even row stride: 16-byte aligned rows (TMA restore)
     if (Ws_out) *Ws_out = Ws;
@@ -167,7 +367,7 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
         } else if (r.status == ST_UNBOUNDED) {
             ev.evaluation = -INFINITY;
         } else {
-            ev.evaluation = t->evaluation;  // stale, unused when infeasible
+            ev.evaluation = 0.0;  // infeasible: never read by the commit loop; rank-independent on the wire
         }
         ev.is_integral = r.is_integral; ev.branch_var = r.branch_var; ev.branch_value = r.branch_value;
     }
@@ -301,8 +501,12 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
                 }
             const bool resident = iterations > 0 && t->saved.valid && t->engine != 1 && t->engine != 2 &&
                                   resident_fits(t, t->saved.H + maxc);
+            const int nslots = (!resident && iterations > 0 && t->saved.valid) ? slots_for(t, t->saved.H + maxc, std::max(K, (int)mine.size())) : 0;
             if (resident && !mine.empty()) {
                 int rc = eval_nodes_resident(t, mine.data(), (int)mine.size(), check_cycles);
+                if (rc) return rc;
+            } else if (nslots >= 2 && mine.size() >= 2) {
+                int rc = eval_nodes_slots(t, mine.data(), (int)mine.size(), nslots, check_cycles);
                 if (rc) return rc;
             } else {
                 for (Branch *b : mine) {

@@ -67,8 +67,9 @@ struct __align__(16) Part {
     int pad;
 };
 
-// Pivot record: the decision carried from one launch to the next.
-struct Rec {
+// Pivot record: the decision carried from one launch to the next.  One 128-byte line (arrays of records,
+// one per node slot, keep the 16-byte loads of k_pivot_step aligned).
+struct __align__(128) Rec {
     int status;      // ST_*
     int phase;       // 1 or 2
     int has_pivot;   // (r, c) is selected and staged but not executed yet
@@ -691,6 +692,8 @@ __device__ __noinline__ void cta_price_next(const TabDev &T, Rec *rec, SelSmem &
 __global__ void __launch_bounds__(512) k_select(const TabDev *Tp, Rec *rec, int force_r, int force_c) {
     __shared__ SelSmem s;
     __shared__ TabDev T;
+    Tp += blockIdx.x;   // one CTA per tableau: node slots launch a row of them (jslp_slots.cuh)
+    rec += blockIdx.x;
     if (threadIdx.x == 0) T = *Tp;
     __syncthreads();
     if (force_r >= 0) {

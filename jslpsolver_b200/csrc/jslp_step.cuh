@@ -941,6 +941,11 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     __shared__ double s_coef[32];
     __shared__ long long s_t0;
     const int tid = threadIdx.x, NT = blockDim.x;
+    // blockIdx.y = node slot (jslp_slots.cuh): every slot has its own descriptor, record and prow side buffer
+    // (stride_arg doubles apart); a single-tableau launch has gridDim.y == 1.
+    Tp += blockIdx.y;
+    rec += blockIdx.y;
+    prow_arg += (size_t)blockIdx.y * (size_t)stride_arg;
     // Programmatic dependent launch: let the next step's CTAs be scheduled while this grid drains,
     // and do not touch anything the previous step wrote before it has completed.  Both are no-ops
     // when the launch carries no programmatic dependency.

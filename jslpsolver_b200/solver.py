@@ -14,6 +14,8 @@ class Solver:
         self.lastSolvedModel: Optional[Model] = None
         self.engine = 0            # JSLP_OPT_ENGINE for every tableau this solver creates
         self.max_spec_batch = 0    # branch-and-cut speculation width (0 = library default)
+        self.node_slots = None     # HBM-resident node batch width (None = auto, 0 = one node at a time)
+        self.slot_steps = None
 
     def Solve(self, model: Any, precision: Optional[float] = None, full: bool = False, validate: bool = False):
         if validate:
@@ -36,6 +38,8 @@ class Solver:
             instance = model
         instance.tableau.engine = self.engine
         instance.tableau.max_spec_batch = self.max_spec_batch
+        instance.tableau.node_slots = self.node_slots
+        instance.tableau.slot_steps = self.slot_steps
         solution = instance.solve()
         self.lastSolvedModel = instance
         solution.solutionSet = solution.generateSolutionSet()

@@ -120,6 +120,8 @@ class GpuTableau:
         self.engine = 0
         self.max_spec_batch = 0
         self.distributed = False  # True: branchAndCut shards node rounds over torch.distributed ranks
+        self.node_slots = None    # JSLP_OPT_NODE_SLOTS (None = library default: auto)
+        self.slot_steps = None    # JSLP_OPT_SLOT_STEPS
         self._cache: dict = {}
         self._cache_log = None
 
@@ -307,6 +309,10 @@ class GpuTableau:
                 opts.rank, opts.n_ranks = D.rank_and_world()
                 opts.all_gather, keep = D.make_all_gather_hook()
         opts.max_nodes = int(getattr(m, "max_nodes", 0) or 0)
+        if self.node_slots is not None:
+            self.set_option(_lib.OPT_NODE_SLOTS, self.node_slots)
+        if self.slot_steps is not None:
+            self.set_option(_lib.OPT_SLOT_STEPS, self.slot_steps)
         st = BnbStatus()
         cap = 4096
         best = (Cut * cap)()

@@ -78,6 +78,12 @@ def main():
                 inst.max_nodes = max_nodes
                 inst.tableau.distributed = world > 1
                 inst.tableau.max_spec_batch = K
+                if os.environ.get("NODE_SLOTS"):
+                    inst.tableau.node_slots = int(os.environ["NODE_SLOTS"])
+                if os.environ.get("SLOT_STEPS"):
+                    inst.tableau.slot_steps = int(os.environ["SLOT_STEPS"])
+                if os.environ.get("STEP_VARIANT"):
+                    inst.tableau.set_option(4, int(os.environ["STEP_VARIANT"]))
                 # the idle B200 sits at 120 MHz: keep the SMs busy right up to the timed solve so the
                 # clock governor has ramped (a 20 ms solve of ~100 us kernels never ramps it by itself)
                 t_w = time.perf_counter()
@@ -96,7 +102,8 @@ def main():
                        "committed_nodes_per_s": b.iterations / (b.gpu_ms * 1e-3), "result": sol.evaluation,
                        "host_eval_ms": b.host_eval_ms, "host_commit_ms": b.host_commit_ms,
                        "host_root_ms": b.host_root_ms, "host_final_ms": b.host_final_ms,
-                       "node_kernel_ms": b.node_kernel_ms}
+                       "node_kernel_ms": b.node_kernel_ms, "node_slots": os.environ.get("NODE_SLOTS", "auto"),
+                       "slot_steps": os.environ.get("SLOT_STEPS", "default")}
                 # node phase = everything after the (unsharded) root relaxation
                 tot = torch.tensor([float(b.nodes_evaluated)], device="cpu" if one_gpu else "cuda")
                 if world > 1:

@@ -245,7 +245,10 @@ def test_row_capacity_growth():
 # ------------------------------------------------------------------ branch and cut
 # (engine, speculation width): HBM path one node at a time (the reference's literal order), then
 # speculative rounds with shared-memory-resident node batches
-BNB_MODES = {"hbm_seq": (2, 1), "auto_seq": (0, 1), "auto_spec8": (0, 8), "auto_spec32": (0, 32), "hbm_spec4": (2, 4)}
+# (engine, speculation width[, node slots, pivots per slot per poll]): "hbm_spec4" runs its rounds in HBM node
+# slots (K3, jslp_slots.cuh), the two "slots" modes force odd slot counts / tiny poll windows
+BNB_MODES = {"hbm_seq": (2, 1), "auto_seq": (0, 1), "auto_spec8": (0, 8), "auto_spec32": (0, 32), "hbm_spec4": (2, 4),
+             "hbm_slots3_steps5": (2, 16, 3, 5), "hbm_noslots_spec4": (2, 4, 0, 32)}
 
 
 @pytest.mark.parametrize("mode", list(BNB_MODES))
@@ -256,7 +259,7 @@ def test_mip_fixture_node_sequence(fx, mode):
     whatever the speculation width or evaluation back-end."""
     import jslpsolver_b200 as J
     from oracle import ref_model
-    if fx["file"] == "Monster_II.json" and mode not in ("hbm_seq", "auto_spec8"):
+    if fx["file"] == "Monster_II.json" and mode not in ("hbm_seq", "auto_spec8", "hbm_slots3_steps5"):
         pytest.skip("large MIP: covered by two modes")
     if fx["file"] == "Vendor Selection.json" and mode != "auto_spec32":
         pytest.skip("long MIP: covered by one mode")
@@ -265,7 +268,9 @@ def test_mip_fixture_node_sequence(fx, mode):
     if osol.tableau is None:
         pytest.skip("decided by presolve")
     s = J.Solver()
-    s.engine, s.max_spec_batch = BNB_MODES[mode]
+    s.engine, s.max_spec_batch = BNB_MODES[mode][:2]
+    if len(BNB_MODES[mode]) > 2:
+        s.node_slots, s.slot_steps = BNB_MODES[mode][2:]
     gsol = s.Solve(jm, full=True)
     gt = gsol._tableau
     onl, gnl = osol.tableau.node_log(), gt.node_log()
