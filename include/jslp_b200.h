@@ -78,7 +78,7 @@ enum {
     JSLP_OPT_BATCH = 2,        /* pivots enqueued per host poll (default 256)              */
     JSLP_OPT_PIVOT_LOG_CAP = 3, /* keep a host-side (row,col,leaving,entering) log, 0 = off */
     /* tuning / diagnostics of the fused pivot step (no effect on results) */
-    JSLP_OPT_STEP_VARIANT = 4, /* kernel instantiation: threads, occupancy, rows per pass, prefetch */
+    JSLP_OPT_STEP_VARIANT = 4, /* kernel instantiation: threads, occupancy, rows per pass, prefetch; -1 = auto */
     JSLP_OPT_GRID_PER_SM = 5,  /* CTAs per SM of the fused step, 0 = the variant's default        */
     JSLP_OPT_LOOKAHEAD = 6,    /* 1 (default) = look-ahead ratio test, 0 = generic serial tail    */
     JSLP_OPT_TIMELINE = 7,     /* record a per-CTA timeline for the first N launches of a solve   */
@@ -87,7 +87,8 @@ enum {
     /* branch-and-cut nodes too large for shared memory (no effect on results) */
     JSLP_OPT_NODE_SLOTS = 10,  /* node LPs in flight side by side in HBM: -1 = auto (default), 0 = one at a
                                   time (the reference's literal applyCuts sequence), n = at most n slots */
-    JSLP_OPT_SLOT_STEPS = 11   /* pivots per slot between host polls of the slot batch (default 32)   */
+    JSLP_OPT_SLOT_STEPS = 11,  /* pivots per slot between host polls of the slot batch (default 32)   */
+    JSLP_OPT_SLOT_VARIANT = 12 /* kernel instantiation used by the slot batch (JSLP_OPT_STEP_VARIANT values) */
 };
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
 /* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */

@@ -11,7 +11,7 @@ _LIB = None
 
 OPT_ENGINE, OPT_BATCH, OPT_PIVOT_LOG_CAP = 1, 2, 3
 OPT_STEP_VARIANT, OPT_GRID_PER_SM, OPT_LOOKAHEAD, OPT_TIMELINE, OPT_PDL, OPT_PINGPONG = 4, 5, 6, 7, 8, 9
-OPT_NODE_SLOTS, OPT_SLOT_STEPS = 10, 11
+OPT_NODE_SLOTS, OPT_SLOT_STEPS, OPT_SLOT_VARIANT = 10, 11, 12
 ENGINE_AUTO, ENGINE_TWO_KERNEL, ENGINE_FUSED, ENGINE_PERSISTENT, ENGINE_RESIDENT = 0, 1, 2, 3, 4
 
 

@@ -139,7 +139,7 @@ struct jslp_tab {
     int isIntegralFlag = 0, bncIterations = 0;
     // options
     int engine = 0, batch = 256;
-    int variant = 1, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0, pingpong = 1;
+    int variant = -1 /* auto */, grid_per_sm = 0, lookahead = 1, timeline_cap = 0, part_cap = 0, g_variant = -1, pdl = 0, pingpong = 1;
     int64_t host_log_cap = 0;
     std::vector<int4> host_log;
     // graphs
@@ -155,6 +155,7 @@ struct jslp_tab {
     NodeSlots slots;        // K3: HBM-resident node batch (jslp_slots.cuh)
     int node_slots = -1;    // JSLP_OPT_NODE_SLOTS: -1 = auto, 0 = off (one node at a time), n = at most n slots
     int slot_steps = 32;    // pivots per slot per host poll
+    int slot_variant = 11;  // kernel instantiation of the slot batch (flat streaming: the batch is HBM-bound)
     long long node_kernel_ns = 0;  // sum over rounds of the slowest node CTA (reporting)
 };
 
@@ -377,6 +378,8 @@ extern "C" int jslp_tab_upload(jslp_tab *t, const double *matrix, const int32_t 
     return JSLP_OK;
 }
 
+static int n_step_variants();
+
 extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
     if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
     switch (key) {
@@ -393,8 +396,8 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
             t->host_log.clear();
             return JSLP_OK;
         case JSLP_OPT_STEP_VARIANT:
-            if (value < 0 || value >= 10) return fail(JSLP_E_INVALID, "step variant out of range");
-            t->variant = (int)value;
+            if (value < -1 || value >= n_step_variants()) return fail(JSLP_E_INVALID, "step variant out of range");
+            t->variant = (int)value;  // -1 = auto
             return JSLP_OK;
         case JSLP_OPT_GRID_PER_SM:
             if (value < 0 || value > 16) return fail(JSLP_E_INVALID, "grid per SM must be 0..16");
@@ -412,6 +415,10 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
         case JSLP_OPT_NODE_SLOTS:
             if (value < -1 || value > 64) return fail(JSLP_E_INVALID, "node slots must be -1..64");
             t->node_slots = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_SLOT_VARIANT:
+            if (value < 0 || value >= n_step_variants()) return fail(JSLP_E_INVALID, "slot variant out of range");
+            t->slot_variant = (int)value;
             return JSLP_OK;
         case JSLP_OPT_SLOT_STEPS:
             if (value < 1 || value > 1024) return fail(JSLP_E_INVALID, "slot steps must be 1..1024");
@@ -461,11 +468,23 @@ static const StepVariant STEP_VARIANTS[] = {
     {JSLP_VARIANT(256, 2, 2, true), "t256 occ2 rc2 prefetch"},
     {JSLP_VARIANT(256, 1, 8, false), "t256 occ1 rc8"},
     {JSLP_VARIANT(512, 1, 4, false), "t512 occ1 rc4"},
+    {JSLP_VARIANT(256, 2, -4, true), "t256 occ2 flat4 prefetch"},
+    {JSLP_VARIANT(256, 2, -8, true), "t256 occ2 flat8 prefetch"},
+    {JSLP_VARIANT(256, 3, -4, true), "t256 occ3 flat4 prefetch"},
+    {JSLP_VARIANT(256, 4, -2, true), "t256 occ4 flat2 prefetch"},
 };
 static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VARIANTS[0]));
+static int n_step_variants() { return N_STEP_VARIANTS; }
 static const int SMALL_BATCH = 24;  // steps in the first graph of a solve
 
-static const StepVariant &step_variant(const jslp_tab *t) { return STEP_VARIANTS[t->variant]; }
+// Auto: while the ping-pong pair fits L2 (126 MB; measured: up to 2 x 32 MB at 2001^2) the per-row loop with
+// prefetch is fastest; once the pair spills to HBM the flat loop with 8 + 8 loads in flight per thread wins
+// (dense 3000^2: 26.8 vs 31.1 us per pivot, profiles/r02_variants.md).
+static int variant_index(const jslp_tab *t) {
+    if (t->variant >= 0) return t->variant;
+    return 16.0 * (double)t->rowcap * t->stride > 0.62 * (double)t->ctx->l2_bytes ? 11 : 1;
+}
+static const StepVariant &step_variant(const jslp_tab *t) { return STEP_VARIANTS[variant_index(t)]; }
 
 static int step_grid(const jslp_tab *t) {
     const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : step_variant(t).ctas_per_sm;
@@ -517,7 +536,7 @@ static int build_graphs(jslp_tab *t) {
     const int smem = t->stride * 8;
     int rc = ensure_step_bufs(t, grid);
     if (rc) return rc;
-    const int key = t->variant + 100 * (t->pdl == 1) + 1000 * (use_pp(t) ? 1 : 0);
+    const int key = variant_index(t) + 100 * (t->pdl == 1) + 1000 * (use_pp(t) ? 1 : 0);
     if (t->g_batch == t->batch && t->g_grid == grid && t->g_smem == smem && t->g_variant == key) return JSLP_OK;
     drop_graphs(t);
     CK(cudaFuncSetAttribute(step_variant(t).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

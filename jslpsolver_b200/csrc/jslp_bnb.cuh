@@ -72,7 +72,7 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
 static int slots_for(const jslp_tab *t, int rowcap, int want) {
     if (t->node_slots == 0 || want < 2) return 0;
     if (!(t->pingpong && t->lookahead && t->nOpt == 0) || t->engine == 1) return 0;
-    const StepVariant &sv = step_variant(t);
+    const StepVariant &sv = STEP_VARIANTS[t->slot_variant];
     const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
     const int C = t->ctx->num_sms * per_sm;
     int geom = 0;
@@ -95,7 +95,7 @@ static int ensure_slots(jslp_tab *t, int B, int need_rowcap) {
     NodeSlots &ns = t->slots;
     jslp_ctx *ctx = t->ctx;
     cudaStream_t s = ctx->stream;
-    const StepVariant &sv = step_variant(t);
+    const StepVariant &sv = STEP_VARIANTS[t->slot_variant];
     const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
     const int G = ctx->num_sms * per_sm / B - 2;
     const int S = t->slot_steps;
@@ -152,7 +152,7 @@ static int ensure_slots(jslp_tab *t, int B, int need_rowcap) {
         ns.key = -1;
     }
     // the graph bakes in the launch geometry and the snapshot it restores from
-    const int key = (int)((((size_t)t->saved.M >> 4) * 2654435761u) ^ (size_t)(t->variant * 131 + G * 7 + S * 1009 + t->saved.H * 31 +
+    const int key = (int)((((size_t)t->saved.M >> 4) * 2654435761u) ^ (size_t)(t->slot_variant * 131 + G * 7 + S * 1009 + t->saved.H * 31 +
                           t->saved.lastElementIndex * 17 + B)) & 0x7fffffff;
     if (ns.graph && ns.key == key && ns.G == G && ns.steps == S) return JSLP_OK;
     if (ns.graph) { cudaGraphExecDestroy(ns.graph); ns.graph = nullptr; }

@@ -345,6 +345,58 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
     }
 }
 
+// Flat form of update_rows_pp for tableaux whose rows are short next to the CTA (config 5: 520 column pairs
+// against 256 threads -- the per-row loop above runs three dependent load->store rounds per pass, the third
+// with 8 active threads).  Rows are padded to the stride, so the CTA's row block is ONE contiguous run of
+// nr * stride/2 column pairs: thread t owns pairs t, t+NT, t+2NT, ... of that run, K of them in flight plus
+// the next K prefetched, whatever the row length.  (row, pair-in-row) is only needed to pick the pivot-row
+// entry and the row's coefficient from shared memory and advances incrementally.
+template <int K>
+__device__ __forceinline__ void update_rows_pp_flat(const double *src, double *dst, int stride_i, const double *frow,
+                                                    const double *s_coef, int r0, int nr, int rstar, int cstar, double q) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int npair = stride_i >> 1;
+    const double2 *frow2 = reinterpret_cast<const double2 *>(frow);
+    const int cpair = cstar >> 1, codd = cstar & 1;
+    const int total = nr * npair;
+    const double *sb = src + (size_t)r0 * stride_i;
+    double *db = dst + (size_t)r0 * stride_i;
+    const int prel = rstar - r0;  // pivot row relative to the block (outside [0, nr) when it is not ours)
+    int row = 0, c2 = tid;
+    while (c2 >= npair) { c2 -= npair; row++; }
+    double2 cur[K], nxt[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int idx = tid + j * NT;
+        if (idx < total) cur[j] = ld_v2(sb + 2 * (size_t)idx);
+    }
+    for (int i0 = tid; i0 < total; i0 += K * NT) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int idx = i0 + (K + j) * NT;
+            if (idx < total) nxt[j] = ld_v2(sb + 2 * (size_t)idx);
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int idx = i0 + j * NT;
+            if (idx < total) {
+                const double2 f = frow2[c2];
+                double2 nv;
+                if (row == prel) nv = f;  // normalised pivot row
+                else {
+                    const double coef = s_coef[row];
+                    nv = nz16(coef) ? upd2(cur[j], f, nz16(f.x), nz16(f.y), coef, c2 == cpair, codd, q) : cur[j];
+                }
+                st_v2(db + 2 * (size_t)idx, nv);
+            }
+            c2 += NT;
+            while (c2 >= npair) { c2 -= npair; row++; }
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) cur[j] = nxt[j];
+    }
+}
+
 // ---- look-ahead partials as self-validating 16-byte messages -------------------------------------
 // A row CTA publishes the ratio-test partial of its rows with ONE 128-bit store; selectors poll the
 // slots.  Word B carries a 24-bit sequence tag (launch + 1) and a 16-bit checksum of word A, so a
@@ -930,6 +982,8 @@ __device__ __forceinline__ void cta_selector_stage(const TabDev &T, Rec *rec, Se
 // ping-pong path (phase 1, bootstrap, optional objectives) run in place on the first gridDim.x-2 CTAs.
 // prow_arg / stride_arg duplicate TabDev.prow / stride (both immutable after jslp_tab_create) so the
 // TMA copy of the pivot row can be issued before the descriptor has been fetched.
+// RC < 0: the ping-pong step streams with update_rows_pp_flat<-RC> (the in-place instantiation of such a
+// variant uses RC = 4).
 template <int NTHREADS, int MINB, int RC, bool PF, bool PP>
 __global__ void __launch_bounds__(NTHREADS, MINB)
     k_pivot_step(TabDev *Tp, Rec *rec, int do_select, const double *prow_arg, int stride_arg) {
@@ -1103,7 +1157,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
             cta_selector_stage(T, rec, sel, frow, G, rstar, cstar, q, next_c, launch, stop_after);
             if (dbg && tid == 0) t2 = t3 = clock64();
         } else {
-            update_rows_pp<RC, PF>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
+            if constexpr (RC < 0) update_rows_pp_flat<-RC>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
+            else update_rows_pp<RC, PF>(T.M, T.M2, T.stride, frow, s_coef, r0, nr, rstar, cstar, q);
             if (dbg && tid == 0) t3 = clock64();
         }
         if (dbg && tid == 0) {
@@ -1141,7 +1196,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB)
     __syncthreads();
     if (dbg && tid == 0) t1 = clock64();
 
-    update_rows<RC, PF>(T, frow, r0, nr, rstar, cstar, q, b == G - 1);
+    update_rows<(RC < 0 ? 4 : RC), PF>(T, frow, r0, nr, rstar, cstar, q, b == G - 1);
     if (dbg && tid == 0) t2 = clock64();
 
     if (fast && next_c > 0) {

@@ -122,6 +122,7 @@ class GpuTableau:
         self.distributed = False  # True: branchAndCut shards node rounds over torch.distributed ranks
         self.node_slots = None    # JSLP_OPT_NODE_SLOTS (None = library default: auto)
         self.slot_steps = None    # JSLP_OPT_SLOT_STEPS
+        self.options: dict = {}   # JSLP_OPT_* -> value, applied after every upload (tuning aids)
         self._cache: dict = {}
         self._cache_log = None
 
@@ -176,6 +177,8 @@ class GpuTableau:
         self.nInts = 0 if ints is None else len(ints)
         if self.engine:
             self.set_option(_lib.OPT_ENGINE, self.engine)
+        for k, v in self.options.items():
+            self.set_option(k, v)
         self._cache.clear()
         self._cache_log = None
         return self

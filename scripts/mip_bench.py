@@ -83,7 +83,9 @@ def main():
                 if os.environ.get("SLOT_STEPS"):
                     inst.tableau.slot_steps = int(os.environ["SLOT_STEPS"])
                 if os.environ.get("STEP_VARIANT"):
-                    inst.tableau.set_option(4, int(os.environ["STEP_VARIANT"]))
+                    inst.tableau.options[4] = int(os.environ["STEP_VARIANT"])
+                if os.environ.get("SLOT_VARIANT"):
+                    inst.tableau.options[12] = int(os.environ["SLOT_VARIANT"])
                 # the idle B200 sits at 120 MHz: keep the SMs busy right up to the timed solve so the
                 # clock governor has ramped (a 20 ms solve of ~100 us kernels never ramps it by itself)
                 t_w = time.perf_counter()
