@@ -153,6 +153,20 @@ int jslp_download(jslp_tab *tab, double *matrix, double *rhs_col, double *cost_r
 /* Drains the host-side pivot log: 4 int32 per pivot (row, col, leaving var, entering var). */
 int jslp_pivot_log(jslp_tab *tab, int32_t *entries, int cap, int *n);
 
+/* Multi-GPU communicator of the branch-and-cut frontier (one process per GPU).  NCCL is loaded at run time;
+ * without libnccl these calls fail with JSLP_E_UNSUPPORTED and single-GPU use is unaffected.  Rank 0 obtains a
+ * 128-byte unique id and hands it to the other ranks through whatever bootstrap the host has (the N-API host:
+ * its own IPC; the Python mirror: torch.distributed); every rank then creates its communicator.  Replaces
+ * nothing in the reference (it is single-process); carries the two collectives of SURVEY.md 8e.  */
+typedef struct jslp_comm jslp_comm;
+int jslp_comm_unique_id(uint8_t *id128);
+int jslp_comm_create(jslp_ctx *ctx, const uint8_t *id128, int rank, int n_ranks, jslp_comm **out);
+void jslp_comm_destroy(jslp_comm *comm);
+/* The collectives themselves (host buffers in and out, staged through device memory on the context stream):
+ * in-place rank-major all-gather of bytes_per_rank bytes, element-wise all-reduce(min) of n doubles.       */
+int jslp_comm_all_gather(jslp_comm *comm, void *buf, int64_t bytes_per_rank);
+int jslp_comm_all_reduce_min(jslp_comm *comm, double *vals, int n);
+
 /* == BranchAndCutService.branchAndCut (branch-and-cut.ts:54-199). */
 typedef struct {
     double tolerance;        /* model.tolerance                                            */
@@ -166,6 +180,13 @@ typedef struct {
      * layer implements it with torch.distributed/NCCL.  NULL when n_ranks <= 1.            */
     int (*all_gather)(void *user, void *buf, int64_t bytes_per_rank);
     void *user;
+    jslp_comm *comm;        /* NCCL communicator: when set it carries the all-gather of node summaries and the
+                               all-reduce(min) of the incumbent bound, and the hook above is ignored          */
+    int32_t shard_policy;   /* 0 = auto: shard a round over the ranks only when its node LPs run in HBM (nodes
+                               that fit shared memory cost less than a collective: every rank evaluates them
+                               itself); 1 = shard every round                                                */
+    int32_t keep_solutions; /* model.keep_solutions (branch-and-cut.ts:143-153): every incumbent is stored   */
+    double timeout_ms;      /* model.timeout (branch-and-cut.ts:61-63,76), wall clock, 0 = none              */
 } jslp_bnb_opts;
 
 typedef struct {
@@ -184,6 +205,13 @@ typedef struct {
     double host_root_ms;   /* part of host_eval_ms spent on the root relaxation                 */
     double host_final_ms;  /* wall time of the final re-solve of the winning branch             */
     double node_kernel_ms; /* sum over rounds of the slowest node CTA's lifetime (%globaltimer) */
+    int32_t timed_out;     /* the loop ended because Date.now() >= terminalTime (branch-and-cut.ts:76)   */
+    int32_t n_solutions;   /* incumbents stored under keep_solutions (jslp_bnb_solution)                 */
+    int64_t nodes_pruned;  /* speculative node LPs dropped or aborted by the incumbent bound of the round */
+    int64_t collectives;   /* all-gathers + all-reduces issued (n_ranks > 1)                             */
+    int64_t slot_pivots;   /* pivots executed in HBM node slots (jslp_slots.cuh), this rank             */
+    double slot_ms;        /* wall time of the slot-batch graphs, this rank                              */
+    double slot_bytes;     /* algorithmic bytes of those pivots: 16 * H_node * stride each               */
 } jslp_bnb_status;
 
 int jslp_branch_and_cut(jslp_tab *root, const jslp_bnb_opts *opts, jslp_bnb_status *out,
@@ -191,6 +219,11 @@ int jslp_branch_and_cut(jslp_tab *root, const jslp_bnb_opts *opts, jslp_bnb_stat
 /* Per-node trace of the last branch_and_cut: 8 doubles per committed node
  * (iteration, nCuts, feasible, evaluation, integral(-1/0/1), branchVar, branchValue, pivots). */
 int jslp_bnb_node_log(jslp_tab *root, double *entries, int64_t cap, int64_t *n);
+/* model.solutions under keep_solutions (branch-and-cut.ts:143-153): incumbent i of the last branch_and_cut as
+ * the state generateSolutionSet reads (solution.ts:35-60): Tableau.evaluation, height, varIndexByRow[height],
+ * right-hand-side column[height].  `cap` = entries the two arrays can hold.                                */
+int jslp_bnb_solution(jslp_tab *root, int i, double *evaluation, int32_t *height, int32_t *var_index_by_row,
+                      double *rhs_col, int cap);
 
 #ifdef __cplusplus
 }

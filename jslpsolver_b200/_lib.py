@@ -37,7 +37,9 @@ ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 class BnbOpts(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("is_minimization", C.c_int32), ("check_cycles", C.c_int32),
                 ("max_spec_batch", C.c_int32), ("rank", C.c_int32), ("n_ranks", C.c_int32),
-                ("max_nodes", C.c_int64), ("all_gather", ALL_GATHER_FN), ("user", C.c_void_p)]
+                ("max_nodes", C.c_int64), ("all_gather", ALL_GATHER_FN), ("user", C.c_void_p),
+                ("comm", C.c_void_p), ("shard_policy", C.c_int32), ("keep_solutions", C.c_int32),
+                ("timeout_ms", C.c_double)]
 
 
 class BnbStatus(C.Structure):
@@ -46,7 +48,9 @@ class BnbStatus(C.Structure):
         ("nodes_evaluated", C.c_int64), ("pivots", C.c_int64), ("evaluation", C.c_double),
         ("best_possible_eval", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("host_eval_ms", C.c_double), ("host_commit_ms", C.c_double),
-        ("host_root_ms", C.c_double), ("host_final_ms", C.c_double), ("node_kernel_ms", C.c_double)]
+        ("host_root_ms", C.c_double), ("host_final_ms", C.c_double), ("node_kernel_ms", C.c_double),
+        ("timed_out", C.c_int32), ("n_solutions", C.c_int32), ("nodes_pruned", C.c_int64),
+        ("collectives", C.c_int64), ("slot_pivots", C.c_int64), ("slot_ms", C.c_double), ("slot_bytes", C.c_double)]
 
 
 # every symbol include/jslp_b200.h declares: (name, restype, argtypes)
@@ -78,6 +82,12 @@ SYMBOLS = [
     ("jslp_pivot_log", C.c_int, [P, P, C.c_int, C.POINTER(C.c_int)]),
     ("jslp_branch_and_cut", C.c_int, [P, C.POINTER(BnbOpts), C.POINTER(BnbStatus), P, C.c_int]),
     ("jslp_bnb_node_log", C.c_int, [P, P, C.c_int64, C.POINTER(C.c_int64)]),
+    ("jslp_bnb_solution", C.c_int, [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32), P, P, C.c_int]),
+    ("jslp_comm_unique_id", C.c_int, [P]),
+    ("jslp_comm_create", C.c_int, [P, P, C.c_int, C.c_int, C.POINTER(P)]),
+    ("jslp_comm_destroy", None, [P]),
+    ("jslp_comm_all_gather", C.c_int, [P, P, C.c_int64]),
+    ("jslp_comm_all_reduce_min", C.c_int, [P, P, C.c_int]),
 ]
 
 

@@ -151,6 +151,10 @@ struct jslp_tab {
     Saved saved;
     Snapshot snaps[2];  // one restart point per in-flight batch
     std::vector<NodeLogEntry> node_log;
+    struct StoredSolution { double evaluation; std::vector<int> vrow; std::vector<double> rhs; };
+    std::vector<StoredSolution> solutions;  // keep_solutions (branch-and-cut.ts:143-153)
+    int64_t slot_pivots = 0;
+    double slot_ms = 0, slot_bytes = 0;
     ResidentBufs rbufs;
     NodeSlots slots;        // K3: HBM-resident node batch (jslp_slots.cuh)
     int node_slots = -1;    // JSLP_OPT_NODE_SLOTS: -1 = auto, 0 = off (one node at a time), n = at most n slots
@@ -160,7 +164,7 @@ struct jslp_tab {
 };
 
 extern "C" const char *jslp_last_error(void) { return g_err.c_str(); }
-extern "C" int jslp_abi_version(void) { return 1; }
+extern "C" int jslp_abi_version(void) { return 2; }
 
 extern "C" int jslp_ctx_create(int device, void *stream, jslp_ctx **out) {
     if (!out) return fail(JSLP_E_INVALID, "out is NULL");
@@ -1138,4 +1142,5 @@ extern "C" int jslp_pivot_log(jslp_tab *t, int32_t *entries, int cap, int *n) {
     return JSLP_OK;
 }
 
+#include "jslp_comm.cuh"
 #include "jslp_bnb.cuh"

@@ -183,9 +183,41 @@ static int ensure_slots(jslp_tab *t, int B, int need_rowcap) {
     return JSLP_OK;
 }
 
+// What a round shares between ranks while its node LPs are running (n_ranks > 1): element-wise min.
+struct RoundExchange {
+    const jslp_bnb_opts *opts;
+    int n_ranks;
+    std::vector<double> scratch;
+    int64_t collectives = 0;
+    int min(double *v, int n) {
+        collectives++;
+        if (opts->comm) return jslp_comm_all_reduce_min(opts->comm, v, n);
+        scratch.assign((size_t)n * n_ranks, 0.0);
+        memcpy(&scratch[(size_t)opts->rank * n], v, sizeof(double) * n);
+        if (opts->all_gather(opts->user, scratch.data(), (int64_t)sizeof(double) * n)) return fail(JSLP_E_INVALID, "all_gather hook failed");
+        for (int r = 0; r < n_ranks; r++)
+            for (int k = 0; k < n; k++) v[k] = r == 0 ? scratch[k] : std::min(v[k], scratch[(size_t)r * n + k]);
+        return JSLP_OK;
+    }
+    int gather(void *buf, int64_t bytes_per_rank) {
+        collectives++;
+        if (opts->comm) return jslp_comm_all_gather(opts->comm, buf, bytes_per_rank);
+        if (opts->all_gather(opts->user, buf, bytes_per_rank)) return fail(JSLP_E_INVALID, "all_gather hook failed");
+        return JSLP_OK;
+    }
+};
+
 // Evaluates nodes[0..n) in B slots side by side.  Nodes whose pivot log shows a cycle are re-evaluated on the
 // single-tableau HBM path (exact stop-before-the-repeat semantics there).
-static int eval_nodes_slots(jslp_tab *t, jslp_bnb::Branch *const *nodes, int n, int B, int check_cycles) {
+//
+// *U is the incumbent bound of the round: the smallest evaluation of an integral feasible node known so far
+// (committed incumbent, cached results, nodes finished in this call -- on any rank when `ex` is set: one
+// all-reduce(min) per poll keeps the ranks' poll loops in lockstep and shares the bound).  A speculative node
+// whose relaxedEvaluation exceeds it is dropped or aborted: it sorts after the node that set the bound, so by
+// the time the reference's loop pops it bestEvaluation <= U < relaxedEvaluation and it is skipped unevaluated
+// (branch-and-cut.ts:90-92).  Pruned nodes keep ev.valid == false.
+static int eval_nodes_slots(jslp_tab *t, jslp_bnb::Branch *const *nodes, int n, int B, int check_cycles, double *U,
+                            RoundExchange *ex, int64_t *pruned) {
     jslp_ctx *ctx = t->ctx;
     cudaStream_t s = ctx->stream;
     int maxc = 0;
@@ -198,68 +230,97 @@ static int eval_nodes_slots(jslp_tab *t, jslp_bnb::Branch *const *nodes, int n, 
     std::vector<int> node_of((size_t)B, -1), redo;
     std::vector<CycleHist> hist((size_t)2 * B);
     int next = 0, done = 0;
-    while (done < n) {
-        int tot = 0;
-        for (int b = 0; b < B; b++) {
-            if (node_of[b] < 0 && next < n) {
-                const std::vector<jslp_cut> &cuts = nodes[next]->cuts;
-                if (tot + (int)cuts.size() > ns.cuts_cap) return fail(JSLP_E_CAPACITY, "slot cut buffer overflow");
-                ns.h_ctl[b] = SlotCtl{SLOT_LOAD, (int)cuts.size(), tot, 0};
-                for (const jslp_cut &c : cuts) {
-                    ns.h_cuts[tot].type = c.type; ns.h_cuts[tot].var_index = c.var_index; ns.h_cuts[tot].value = c.value;
-                    tot++;
+    auto account = [&](int i, int pivots) {
+        t->slot_pivots += pivots;
+        t->slot_bytes += 16.0 * (double)(t->saved.H + (int)nodes[i]->cuts.size()) * t->stride * pivots;
+    };
+    bool any = n > 0 || ex != nullptr;
+    while (any) {
+        if (done < n) {
+            int tot = 0;
+            for (int b = 0; b < B; b++) {
+                if (node_of[b] >= 0 && nodes[node_of[b]]->relaxedEvaluation > *U) {  // abort: the reference skips it
+                    account(node_of[b], ns.h_out[b].rec.p1 + ns.h_out[b].rec.p2);
+                    node_of[b] = -1; done++; (*pruned)++;
                 }
-                node_of[b] = next++;
-                hist[2 * b] = CycleHist(); hist[2 * b + 1] = CycleHist();
-            } else {
-                ns.h_ctl[b].cmd = node_of[b] >= 0 ? SLOT_CONTINUE : SLOT_IDLE;
-            }
-        }
-        const auto t_g = std::chrono::steady_clock::now();
-        CK(cudaGraphLaunch(ns.graph, s));
-        ctx->launches += 3 + S;
-        CK(cudaStreamSynchronize(s));
-        if (dbg) {
-            int running = 0, loads = 0;
-            for (int b = 0; b < B; b++) { running += node_of[b] >= 0; loads += ns.h_ctl[b].cmd == SLOT_LOAD; }
-            fprintf(stderr, "slot graph: B %d G %d S %d running %d loads %d: %.0f us\n", B, ns.G, S, running, loads,
-                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_g).count());
-        }
-        for (int b = 0; b < B; b++) {
-            const int i = node_of[b];
-            if (i < 0) continue;
-            const Rec &r = ns.h_out[b].rec;
-            if (r.status == ST_ERROR) return fail(JSLP_E_CUDA, "slot batch: selector CTA timed out waiting for row CTAs");
-            if (r.log_n > S + 2) return fail(JSLP_E_CAPACITY, "slot pivot log overflow inside one batch");
-            bool hit = false;
-            if (check_cycles) {
-                const int4 *lg = ns.h_logs + (size_t)b * (S + 2);
-                int cs, cl;
-                for (int k = 0; k < r.log_n && !hit; k++) {
-                    CycleHist &h = hist[2 * b + (((lg[k].x >> 30) & 1) ? 1 : 0)];
-                    hit = h.push_and_check(((long long)lg[k].z << 32) | (unsigned int)lg[k].w, &cs, &cl);
+                while (node_of[b] < 0 && next < n && nodes[next]->relaxedEvaluation > *U) { next++; done++; (*pruned)++; }
+                if (node_of[b] < 0 && next < n) {
+                    const std::vector<jslp_cut> &cuts = nodes[next]->cuts;
+                    if (tot + (int)cuts.size() > ns.cuts_cap) return fail(JSLP_E_CAPACITY, "slot cut buffer overflow");
+                    ns.h_ctl[b] = SlotCtl{SLOT_LOAD, (int)cuts.size(), tot, 0};
+                    for (const jslp_cut &c : cuts) {
+                        ns.h_cuts[tot].type = c.type; ns.h_cuts[tot].var_index = c.var_index; ns.h_cuts[tot].value = c.value;
+                        tot++;
+                    }
+                    node_of[b] = next++;
+                    hist[2 * b] = CycleHist(); hist[2 * b + 1] = CycleHist();
+                } else {
+                    ns.h_ctl[b].cmd = node_of[b] >= 0 ? SLOT_CONTINUE : SLOT_IDLE;
                 }
             }
-            if (hit) { redo.push_back(i); node_of[b] = -1; done++; continue; }
-            if (r.status == ST_RUNNING) continue;
-            jslp_bnb::NodeEval &ev = nodes[i]->ev;
-            ev.valid = true;
-            ev.pivots = r.p1 + r.p2;
-            ev.optimal = r.status == ST_OPTIMAL;
-            ev.bounded = r.status != ST_UNBOUNDED;
-            ev.feasible = r.status == ST_OPTIMAL || r.status == ST_UNBOUNDED;
-            ev.evaluation = r.status == ST_OPTIMAL ? jslp_round_evaluation(r.eval_raw, t->precision)
-                                                   : (r.status == ST_UNBOUNDED ? -INFINITY : 0.0);
-            const MipOut &mo = ns.h_out[b].mip;
-            ev.is_integral = ev.feasible ? mo.is_integral : 0;
-            ev.branch_var = ev.feasible ? mo.var_index : -1;
-            ev.branch_value = ev.feasible ? mo.value : 0.0;
-            if (dbg) fprintf(stderr, "slot node: slot %d cuts %d pivots %d+%d status %d\n", b, (int)nodes[i]->cuts.size(), r.p1, r.p2, r.status);
-            node_of[b] = -1;
-            done++;
+        }
+        int running = 0;
+        for (int b = 0; b < B; b++) running += node_of[b] >= 0;
+        if (running > 0) {
+            const auto t_g = std::chrono::steady_clock::now();
+            CK(cudaGraphLaunch(ns.graph, s));
+            ctx->launches += 3 + S;
+            CK(cudaStreamSynchronize(s));
+            const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_g).count();
+            t->slot_ms += 1e-3 * us;
+            if (dbg) {
+                int loads = 0;
+                for (int b = 0; b < B; b++) loads += ns.h_ctl[b].cmd == SLOT_LOAD;
+                fprintf(stderr, "slot graph: B %d G %d S %d running %d loads %d: %.0f us\n", B, ns.G, S, running, loads, us);
+            }
+            for (int b = 0; b < B; b++) {
+                const int i = node_of[b];
+                if (i < 0) continue;
+                const Rec &r = ns.h_out[b].rec;
+                if (r.status == ST_ERROR) return fail(JSLP_E_CUDA, "slot batch: selector CTA timed out waiting for row CTAs");
+                if (r.log_n > S + 2) return fail(JSLP_E_CAPACITY, "slot pivot log overflow inside one batch");
+                bool hit = false;
+                if (check_cycles) {
+                    const int4 *lg = ns.h_logs + (size_t)b * (S + 2);
+                    int cs, cl;
+                    for (int k = 0; k < r.log_n && !hit; k++) {
+                        CycleHist &h = hist[2 * b + (((lg[k].x >> 30) & 1) ? 1 : 0)];
+                        hit = h.push_and_check(((long long)lg[k].z << 32) | (unsigned int)lg[k].w, &cs, &cl);
+                    }
+                }
+                if (hit) { account(i, r.p1 + r.p2); redo.push_back(i); node_of[b] = -1; done++; continue; }
+                if (r.status == ST_RUNNING) continue;
+                jslp_bnb::NodeEval &ev = nodes[i]->ev;
+                ev.valid = true;
+                ev.pivots = r.p1 + r.p2;
+                ev.optimal = r.status == ST_OPTIMAL;
+                ev.bounded = r.status != ST_UNBOUNDED;
+                ev.feasible = r.status == ST_OPTIMAL || r.status == ST_UNBOUNDED;
+                ev.evaluation = r.status == ST_OPTIMAL ? jslp_round_evaluation(r.eval_raw, t->precision)
+                                                       : (r.status == ST_UNBOUNDED ? -INFINITY : 0.0);
+                const MipOut &mo = ns.h_out[b].mip;
+                ev.is_integral = ev.feasible ? mo.is_integral : 0;
+                ev.branch_var = ev.feasible ? mo.var_index : -1;
+                ev.branch_value = ev.feasible ? mo.value : 0.0;
+                if (ev.feasible && ev.is_integral && ev.evaluation < *U) *U = ev.evaluation;
+                account(i, ev.pivots);
+                if (dbg) fprintf(stderr, "slot node: slot %d cuts %d pivots %d+%d status %d\n", b, (int)nodes[i]->cuts.size(), r.p1, r.p2, r.status);
+                node_of[b] = -1;
+                done++;
+            }
+        }
+        if (ex) {  // share the bound; stay in the loop until every rank has finished its nodes
+            double v[2] = {*U, done < n ? -1.0 : 0.0};
+            rc = ex->min(v, 2);
+            if (rc) return rc;
+            *U = v[0];
+            any = v[1] < 0;
+        } else {
+            any = done < n;
         }
     }
     for (int i : redo) {
+        if (nodes[i]->relaxedEvaluation > *U) { (*pruned)++; continue; }
         rc = eval_node_streaming(t, *nodes[i], check_cycles, nodes[i]->ev);
         if (rc) return rc;
     }
@@ -380,28 +441,54 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
     if (!t || !opts) return fail(JSLP_E_INVALID, "NULL argument");
     if (t->n_int <= 0) return fail(JSLP_E_INVALID, "branch_and_cut needs integer variables (upload int_var_indices)");
     const int n_ranks = std::max(1, opts->n_ranks), rank = opts->rank;
-    if (n_ranks > 1 && !opts->all_gather) return fail(JSLP_E_INVALID, "n_ranks > 1 needs an all_gather hook");
+    if (n_ranks > 1 && !opts->all_gather && !opts->comm) return fail(JSLP_E_INVALID, "n_ranks > 1 needs a communicator or an all_gather hook");
     if (n_ranks > 1 && t->nOpt > 7) return fail(JSLP_E_UNSUPPORTED, "more than 7 optional objectives across ranks");
     jslp_ctx *ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const auto t_start = now();
+    const double timeout_ms = opts->timeout_ms > 0 ? opts->timeout_ms : 0;  // branch-and-cut.ts:61-63
+    auto time_up = [&] { return timeout_ms > 0 && ms_since(t_start) >= timeout_ms; };
 
     Frontier branches;
     int iterations = 0, rounds = 0;
     const double tolerance = opts->tolerance;
     const int check_cycles = opts->check_cycles;
-    bool toleranceFlag = true;
+    bool toleranceFlag = true, timed_out = false;
     double bestEvaluation = INFINITY;
     std::unique_ptr<Branch> bestBranch, lastCommitted;
     std::vector<double> bestOpt((size_t)t->nOpt, INFINITY);
-    int64_t pivots = 0, nodes = 0;
+    int64_t pivots = 0, nodes = 0, pruned = 0;
     t->node_log.clear();
+    t->solutions.clear();
     t->saved.valid = false;
     t->isIntegralFlag = 0;
-    bool early_return = false, speculated = false;
+    t->slot_pivots = 0; t->slot_ms = 0; t->slot_bytes = 0;
+    bool early_return = false;
     int K = opts->max_spec_batch > 0 ? opts->max_spec_batch : 16;  // any width commits in the same order
     std::vector<double> wire;
+    RoundExchange ex{opts, n_ranks, {}, 0};
+
+    // keep_solutions (branch-and-cut.ts:143-153): the incumbent's tableau state, as generateSolutionSet reads it.
+    // Node evaluators return summaries only, so the node is solved once more in place (incumbents are rare).
+    auto store_solution = [&](const Branch &b) -> int {
+        NodeEval ev;
+        int rc = eval_node_streaming(t, b, check_cycles, ev);
+        if (rc) return rc;
+        jslp_tab::StoredSolution sol;
+        sol.evaluation = t->evaluation;
+        sol.vrow.resize((size_t)t->H);
+        sol.rhs.resize((size_t)t->H);
+        rc = jslp_download(t, nullptr, sol.rhs.data(), nullptr, sol.vrow.data(), nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        t->solutions.push_back(std::move(sol));
+        return JSLP_OK;
+    };
 
     // commits one evaluated node exactly like one iteration of branch-and-cut.ts:89-192
     auto commit = [&](std::unique_ptr<Branch> active) -> int {
@@ -439,6 +526,10 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             for (int o = 0; o < t->nOpt; o++) bestOpt[o] = ev.opt0[o];
             t->node_log.push_back(nl);
             bestBranch.reset(new Branch{active->relaxedEvaluation, active->cuts, NodeEval()});
+            if (opts->keep_solutions) {
+                int rc = store_solution(*active);
+                if (rc) return rc;
+            }
             lastCommitted = std::move(active);
         } else {
             if (iterations == 1) {  // snapshot = optimal root tableau (branch-and-cut.ts:155-157)
@@ -468,10 +559,6 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
 
     double eval_ms = 0, commit_ms = 0, root_ms = 0, final_ms = 0;
     t->node_kernel_ns = 0;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    };
     branches.push(std::unique_ptr<Branch>(new Branch{-INFINITY, {}, NodeEval()}));
     bool stop = false;
     while (!stop && !branches.empty() && toleranceFlag) {
@@ -479,50 +566,62 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         const int width = iterations == 0 ? 1 : K;  // the root decides everything: alone
         std::vector<Frontier::Entry> taken;
         std::vector<Branch *> todo;
+        // U = incumbent bound of the round (see eval_nodes_slots): committed incumbent and cached integral results
+        double U = bestEvaluation;
         while (!branches.empty() && (int)todo.size() < width) {
             Frontier::Entry e = branches.pop_entry();
             // nodes that will be skipped at pop (branch-and-cut.ts:90-92) stay in the heap -- their pop
             // still consumes a loop iteration of the reference -- but are never evaluated
-            if (!(e.b->relaxedEvaluation > bestEvaluation) && !e.b->ev.valid) todo.push_back(e.b.get());
+            if (e.b->ev.valid) {
+                if (e.b->ev.feasible && e.b->ev.is_integral && e.b->ev.evaluation < U) U = e.b->ev.evaluation;
+            } else if (!(e.b->relaxedEvaluation > U)) {
+                todo.push_back(e.b.get());
+            } else {
+                pruned++;
+            }
             taken.push_back(std::move(e));
         }
         const auto t_eval = now();
         if (!todo.empty()) {
             rounds++;
-            std::vector<Branch *> mine;
-            int maxc = 0;
-            // the root round is NOT sharded: every rank needs the solved root in its own tableau, it is
-            // what jslp_save snapshots and what every later node is derived from
-            const bool sharded = n_ranks > 1 && iterations > 0;
-            for (size_t i = 0; i < todo.size(); i++)
-                if (!sharded || (int)(i % n_ranks) == rank) {
-                    mine.push_back(todo[i]);
-                    maxc = std::max(maxc, (int)todo[i]->cuts.size());
-                }
+            int maxc_all = 0;
+            for (Branch *b : todo) maxc_all = std::max(maxc_all, (int)b->cuts.size());
+            // every rank takes the same decisions from the same (rank-independent) quantities
             const bool resident = iterations > 0 && t->saved.valid && t->engine != 1 && t->engine != 2 &&
-                                  resident_fits(t, t->saved.H + maxc);
-            const int nslots = (!resident && iterations > 0 && t->saved.valid) ? slots_for(t, t->saved.H + maxc, std::max(K, (int)mine.size())) : 0;
-            if (resident && !mine.empty()) {
-                int rc = eval_nodes_resident(t, mine.data(), (int)mine.size(), check_cycles);
-                if (rc) return rc;
-            } else if (nslots >= 2 && mine.size() >= 2) {
-                int rc = eval_nodes_slots(t, mine.data(), (int)mine.size(), nslots, check_cycles);
+                                  resident_fits(t, t->saved.H + maxc_all);
+            const int nslots = (!resident && iterations > 0 && t->saved.valid && todo.size() >= 2)
+                                   ? slots_for(t, t->saved.H + maxc_all, std::max(K, (int)todo.size())) : 0;
+            // The root round is NOT sharded: every rank needs the solved root in its own tableau, it is what
+            // jslp_save snapshots and what every later node is derived from.  Rounds of nodes that fit shared
+            // memory are not sharded either unless asked: a whole round costs less than one collective.
+            const bool sharded = n_ranks > 1 && iterations > 0 && (opts->shard_policy == 1 || !resident);
+            std::vector<Branch *> mine;
+            for (size_t i = 0; i < todo.size(); i++)
+                if (!sharded || (int)(i % n_ranks) == rank) mine.push_back(todo[i]);
+            if (resident) {
+                if (!mine.empty()) {
+                    int rc = eval_nodes_resident(t, mine.data(), (int)mine.size(), check_cycles);
+                    if (rc) return rc;
+                }
+            } else if (nslots >= 2) {
+                int rc = eval_nodes_slots(t, mine.data(), (int)mine.size(), nslots, check_cycles, &U, sharded ? &ex : nullptr, &pruned);
                 if (rc) return rc;
             } else {
                 for (Branch *b : mine) {
+                    if (b->relaxedEvaluation > U) { pruned++; continue; }
                     int rc = eval_node_streaming(t, *b, check_cycles, b->ev);
                     if (rc) return rc;
+                    if (b->ev.feasible && b->ev.is_integral && b->ev.evaluation < U) U = b->ev.evaluation;
                 }
             }
             nodes += (int64_t)mine.size();
-            if (todo.size() > 1) speculated = true;
             if (sharded) {  // all-gather the summaries: rank-major blocks of `per` records
                 const int per = (int)((todo.size() + n_ranks - 1) / n_ranks);
                 wire.assign((size_t)per * n_ranks * WIRE_DOUBLES, 0.0);
                 for (size_t j = 0; j < mine.size(); j++)
                     to_wire(mine[j]->ev, &wire[((size_t)rank * per + j) * WIRE_DOUBLES]);
-                int rc = opts->all_gather(opts->user, wire.data(), (int64_t)per * WIRE_DOUBLES * 8);
-                if (rc) return fail(JSLP_E_INVALID, "all_gather hook failed");
+                int rc = ex.gather(wire.data(), (int64_t)per * WIRE_DOUBLES * 8);
+                if (rc) return rc;
                 for (size_t i = 0; i < todo.size(); i++)
                     from_wire(todo[i]->ev, &wire[((size_t)(i % n_ranks) * per + i / n_ranks) * WIRE_DOUBLES]);
             }
@@ -532,9 +631,21 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         eval_ms += ms_since(t_eval);
         const auto t_commit = now();
 
+        // Date.now() < terminalTime (branch-and-cut.ts:76).  One rank: tested before every commit, like the
+        // reference's loop condition.  Several ranks: tested once per round and agreed on (min-reduce), so that
+        // every rank stops at the same commit.
+        bool round_time_up = false;
+        if (n_ranks > 1 && timeout_ms > 0) {
+            double v = time_up() ? -1.0 : 0.0;
+            int rc = ex.min(&v, 1);
+            if (rc) return rc;
+            round_time_up = v < 0;
+        }
+
         // ---- commit sequentially in the reference's exact order ---------------------------------
         while (!branches.empty() && toleranceFlag) {
             if (opts->max_nodes > 0 && iterations >= opts->max_nodes) { stop = true; break; }
+            if (n_ranks > 1 ? round_time_up : time_up()) { timed_out = true; stop = true; break; }
             const double acceptableThreshold = opts->is_minimization ? t->bestPossibleEval * (1 + tolerance)
                                                                      : t->bestPossibleEval * (1 - tolerance);
             // the reference checks the tolerance BEFORE popping, and still processes that pop
@@ -568,7 +679,6 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             }
             final_ms = ms_since(t_fin);
         }
-        (void)speculated;
         if (bestBranch) {
             n_best = (int)bestBranch->cuts.size();
             if (best_cuts)
@@ -590,7 +700,22 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         out->kernel_launches = ctx->launches - launches0;
         out->host_eval_ms = eval_ms; out->host_commit_ms = commit_ms;
         out->host_root_ms = root_ms; out->host_final_ms = final_ms; out->node_kernel_ms = 1e-6 * (double)t->node_kernel_ns;
+        out->timed_out = timed_out ? 1 : 0; out->n_solutions = (int)t->solutions.size();
+        out->nodes_pruned = pruned; out->collectives = ex.collectives;
+        out->slot_pivots = t->slot_pivots; out->slot_ms = t->slot_ms; out->slot_bytes = t->slot_bytes;
     }
+    return JSLP_OK;
+}
+
+extern "C" int jslp_bnb_solution(jslp_tab *t, int i, double *evaluation, int32_t *height, int32_t *vrow, double *rhs, int cap) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    if (i < 0 || i >= (int)t->solutions.size()) return fail(JSLP_E_INVALID, "solution index out of range");
+    const jslp_tab::StoredSolution &s = t->solutions[(size_t)i];
+    if (evaluation) *evaluation = s.evaluation;
+    if (height) *height = (int32_t)s.vrow.size();
+    const size_t n = std::min<size_t>((size_t)std::max(0, cap), s.vrow.size());
+    if (vrow) memcpy(vrow, s.vrow.data(), sizeof(int32_t) * n);
+    if (rhs) memcpy(rhs, s.rhs.data(), sizeof(double) * n);
     return JSLP_OK;
 }
 

@@ -25,6 +25,42 @@ def rank_and_world():
     return dist.get_rank(), dist.get_world_size()
 
 
+_COMM: dict = {}
+
+
+def nccl_communicator(context):
+    """The in-library NCCL communicator of this process (include/jslp_b200.h: jslp_comm_*), created once per
+    device context: rank 0's 128-byte unique id travels over torch.distributed (the bootstrap this host layer
+    happens to have), then every rank calls jslp_comm_create.  Returns None when the process group is not NCCL
+    (gloo in the CPU tests and when several ranks share one GPU): the caller falls back to the host hook."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() != "nccl":
+        return None
+    key = id(context)
+    if key in _COMM:
+        return _COMM[key][0]
+    from . import _lib
+    L = context.lib
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(L.jslp_comm_unique_id(buf))
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    dist.broadcast(t, 0)
+    ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+    h = C.c_void_p()
+    _lib.check(L.jslp_comm_create(context.handle, ident, rank, world, C.byref(h)))
+    _COMM[key] = (h, context)
+    return h
+
+
+def destroy_communicators():
+    for h, ctx in _COMM.values():
+        ctx.lib.jslp_comm_destroy(h)
+    _COMM.clear()
+
+
 def make_all_gather_hook(device=None):
     """Returns (ctypes callback, keepalive).  The callback all-gathers `bytes_per_rank` bytes per rank
     in place in the rank-major host buffer `buf` (jslp_bnb_opts.all_gather)."""

@@ -120,6 +120,7 @@ class GpuTableau:
         self.engine = 0
         self.max_spec_batch = 0
         self.distributed = False  # True: branchAndCut shards node rounds over torch.distributed ranks
+        self.shard_policy = 0     # jslp_bnb_opts.shard_policy: 0 = shard only rounds whose node LPs run in HBM, 1 = always
         self.node_slots = None    # JSLP_OPT_NODE_SLOTS (None = library default: auto)
         self.slot_steps = None    # JSLP_OPT_SLOT_STEPS
         self.options: dict = {}   # JSLP_OPT_* -> value, applied after every upload (tuning aids)
@@ -310,8 +311,16 @@ class GpuTableau:
             from . import distributed as D
             if D.is_active():
                 opts.rank, opts.n_ranks = D.rank_and_world()
-                opts.all_gather, keep = D.make_all_gather_hook()
+                comm = D.nccl_communicator(self.context)  # in-library NCCL; None under gloo (CPU tests, shared GPU)
+                if comm is not None:
+                    opts.comm = comm
+                else:
+                    opts.all_gather, keep = D.make_all_gather_hook()
+        opts.shard_policy = int(self.shard_policy)
         opts.max_nodes = int(getattr(m, "max_nodes", 0) or 0)
+        # model.timeout [ms] and options.keep_solutions (model.ts:338-374; branch-and-cut.ts:61-63,76,143-153)
+        opts.timeout_ms = float(getattr(m, "timeout", 0) or 0)
+        opts.keep_solutions = int(bool(getattr(m, "keep_solutions", False)))
         if self.node_slots is not None:
             self.set_option(_lib.OPT_NODE_SLOTS, self.node_slots)
         if self.slot_steps is not None:
@@ -328,6 +337,27 @@ class GpuTableau:
             self.__isIntegral = True
         self.bestCuts = [(best[i].type, best[i].var_index, best[i].value) for i in range(min(cap, st.n_best_cuts))]
         self._refresh_dims()
+        if opts.keep_solutions and m is not None:  # branch-and-cut.ts:143-153
+            for i in range(st.n_solutions):
+                m.solutions = (m.solutions or []) + [self._stored_solution(i)]
+
+    def _stored_solution(self, i: int) -> dict:
+        """model.solutions[i]: generateSolutionSet() of incumbent i plus `result` (branch-and-cut.ts:144-152)."""
+        L = self.context.lib
+        ev, h = C.c_double(), C.c_int32()
+        _lib.check(L.jslp_bnb_solution(self._h(), i, C.byref(ev), C.byref(h), None, None, 0))
+        vrow, rhs = np.empty(h.value, dtype=np.int32), np.empty(h.value, dtype=np.float64)
+        _lib.check(L.jslp_bnb_solution(self._h(), i, None, None, vrow.ctypes.data, rhs.ctypes.data, h.value))
+        rounding = js_round(1 / self.precision)
+        store: dict = {}
+        for r in range(1, h.value):
+            var = self.variablesPerIndex.get(int(vrow[r]))
+            if var is None or var.isSlack:
+                continue
+            store[var.id] = js_round((EPSILON + float(rhs[r])) * rounding) / rounding
+        is_min = True if self.model is None else self.model.isMinimization
+        store["result"] = ev.value if is_min else -ev.value
+        return store
 
     def node_log(self) -> np.ndarray:
         n = C.c_int64()

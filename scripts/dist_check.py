@@ -53,6 +53,7 @@ def main():
         for K in (4, 16):
             inst = J.Model().loadJson(jm)
             inst.tableau.distributed = world > 1
+            inst.tableau.shard_policy = 1  # small fixtures fit shared memory: shard them anyway, this is the check
             inst.tableau.max_spec_batch = K
             sol = inst.solve()
             gt = inst.tableau
@@ -72,9 +73,40 @@ def main():
                 print(json.dumps({"fixture": fx["file"], "n_gpus": world, "spec_width": K, "ok_on_all_ranks": ok,
                                   "iterations": b.iterations, "rounds": b.rounds, "node_lps_this_rank": b.nodes_evaluated,
                                   "result": sol.evaluation}), flush=True)
+    # BASELINE config 5 (knapsack 1024 x 512): node LPs in HBM slots, sharded, incumbent bound all-reduced per poll
+    # (NCCL inside the library when the backend is nccl) -- against the oracle's cached first 64 nodes
+    if os.environ.get("DIST_SKIP_KNAPSACK", "0") != "1":
+        from jslpsolver_b200 import problems
+        z = np.load(os.path.join(ROOT, "tests", "golden", "config5_knapsack.npz"))
+        model = problems.knapsack_mip_model(1024, 512, seed=12345)
+        for K in (8, 32):
+            inst = J.Model().loadJson(model)
+            inst.max_nodes = int(z["max_nodes"])
+            inst.tableau.distributed = world > 1
+            inst.tableau.max_spec_batch = K
+            sol = inst.solve()
+            gt = inst.tableau
+            gnl, onl = gt.node_log(), z["node_log"]
+            same = gnl.shape == onl.shape and bool(np.all((gnl == onl) | (np.arange(8)[None, :] == 3) & (onl[:, 2:3] == 0)))
+            import hashlib
+            same = same and hashlib.sha256(np.ascontiguousarray(gt.matrix2d()).tobytes()).hexdigest() == str(z["final_matrix_sha"])
+            flag = torch.tensor([1 if same else 0], device="cpu" if one_gpu else "cuda")
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+            ok_all = ok_all and ok
+            if rank == 0:
+                b = gt.lastBnbStatus
+                print(json.dumps({"fixture": "config 5 knapsack, first 64 nodes", "n_gpus": world, "spec_width": K,
+                                  "ok_on_all_ranks": ok, "iterations": b.iterations, "rounds": b.rounds,
+                                  "node_lps_this_rank": b.nodes_evaluated, "collectives": b.collectives,
+                                  "gpu_ms": b.gpu_ms, "root_ms": b.host_root_ms}), flush=True)
+            gt.close()
     if rank == 0:
         print("DIST_CHECK OK" if ok_all else "DIST_CHECK FAILED", flush=True)
     if world > 1:
+        from jslpsolver_b200 import distributed as D
+        D.destroy_communicators()
         dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
 

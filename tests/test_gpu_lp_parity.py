@@ -286,3 +286,62 @@ def test_mip_fixture_node_sequence(fx, mode):
     assert same_bits(gt.matrix2d(), osol.tableau.matrix())
     assert np.array_equal(gt.varIndexByRow, osol.tableau.maps()[0])
     assert [(a, b, float(c)) for a, b, c in gt.bestCuts] == [(a, b, float(c)) for a, b, c in osol.tableau.best_cuts()]
+
+
+# ------------------------------------------------------------------ timeout / keep_solutions (branch-and-cut.ts:61-63,76,143-153)
+def _fixture(name):
+    return [f for f in BUNDLE["fixtures"] if f["file"] == name][0]
+
+
+def test_timeout_stops_the_loop_with_the_incumbent_so_far():
+    """model.timeout is wall clock (Date.now() < terminalTime before every iteration): whatever prefix of the loop ran
+    must be the reference's prefix, and the result keeps the reference's shape.  A generous timeout changes nothing."""
+    import jslpsolver_b200 as J
+    from oracle import ref_model
+    jm = strip_timeouts(_fixture("LargeFarmMIP.json")["model"])
+    osol = ref_model.solve_full(jm, fast_cycles=True, node_log=1 << 20)
+    onl = osol.tableau.node_log()
+    full = J.Solve(dict(jm, timeout=600000))
+    assert full == ref_model.Solve(jm, fast_cycles=True)
+    for tmo in (0.5, 2.0, 5.0):
+        s = J.Solver()
+        s.max_spec_batch = 4
+        gsol = s.Solve(dict(jm, timeout=tmo), full=True)
+        gt = gsol._tableau
+        b = gt.lastBnbStatus
+        gnl = gt.node_log()
+        assert len(gnl) == b.iterations <= len(onl)
+        assert np.array_equal(gnl[:, [0, 1, 2, 4, 5, 7]], onl[:len(gnl), [0, 1, 2, 4, 5, 7]])
+        if b.iterations < len(onl):
+            assert b.timed_out == 1
+        res = s._simplified(gsol)
+        assert list(res)[:3] == ["feasible", "result", "bounded"] or "feasible" in res
+        incumbents = [r for r in gnl if r[4] == 1]
+        if incumbents:  # the winner is re-solved: the tableau holds the best incumbent so far
+            assert same_bits(gt.evaluation, incumbents[-1][3]) and res.get("isIntegral") is True
+    assert b.timed_out in (0, 1)
+
+
+def test_keep_solutions_stores_every_incumbent():
+    """options.keep_solutions: model.solutions gets one {var: value, ..., result} per incumbent, in order."""
+    import jslpsolver_b200 as J
+    from oracle import ref_model
+    for name in ("LargeFarmMIP.json", "Knapsack 1.json", "Monster_II.json"):
+        jm = strip_timeouts(_fixture(name)["model"])
+        jm["options"] = dict(jm.get("options") or {}, keep_solutions=True)
+        osol = ref_model.solve_full(jm, fast_cycles=True, node_log=1 << 20)
+        onl = osol.tableau.node_log()
+        s = J.Solver()
+        gsol = s.Solve(jm, full=True)
+        m = s.lastSolvedModel
+        incumbents = [r for r in onl if r[4] == 1 and r[0] > 1]
+        assert len(m.solutions or []) == len(incumbents), name
+        sign = 1.0 if m.isMinimization else -1.0
+        for sol, r in zip(m.solutions, incumbents):
+            assert same_bits(sol["result"], sign * r[3]) or sol["result"] == sign * r[3]
+        if incumbents:
+            last = dict(m.solutions[-1])
+            assert last.pop("result") == gsol.evaluation
+            final = {k: v for k, v in gsol.solutionSet.items()}
+            assert last == final, name
+        assert s._simplified(gsol) == ref_model.Solve(jm, fast_cycles=True)

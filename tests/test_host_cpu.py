@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == bound, (declared ^ bound)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.jslp_abi_version() == 1
+    assert L.jslp_abi_version() == 2
 
 
 def test_library_contains_sm100a_code():
