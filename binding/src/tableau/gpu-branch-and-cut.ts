@@ -1,0 +1,27 @@
+/**
+ * @file src/tableau/gpu-branch-and-cut.ts  (drop into the reference tree next to branch-and-cut.ts)
+ * @description BranchAndCutService (branch-and-cut.ts:19-22) backed by the B200 frontier manager.
+ *
+ * `solver.branchAndCutService` / `selectBranchAndCutService` (src/main.ts:48-49,62-83) may return this service for
+ * models without nodeSelection / branching / useIncremental options; both members delegate to GpuTableau, so a
+ * plain host Tableau passed in by other callers falls back to the reference service.
+ */
+import type Tableau from "./tableau";
+import type { BranchCut } from "./types";
+import type { BranchAndCutService } from "./branch-and-cut";
+import { createBranchAndCutService } from "./branch-and-cut";
+import GpuTableau from "./gpu-tableau";
+
+export function createGpuBranchAndCutService(): BranchAndCutService {
+    const host = createBranchAndCutService();
+    return {
+        applyCuts(tableau: Tableau, cuts: BranchCut[]): void {
+            if (tableau instanceof GpuTableau) GpuTableau.prototype.applyCuts.call(tableau, cuts);
+            else host.applyCuts(tableau, cuts);
+        },
+        branchAndCut(tableau: Tableau): void {
+            if (tableau instanceof GpuTableau) GpuTableau.prototype.branchAndCut.call(tableau);
+            else host.branchAndCut(tableau);
+        },
+    };
+}

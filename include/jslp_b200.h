@@ -93,6 +93,10 @@ enum {
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
 /* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */
 int jslp_debug_timeline(jslp_tab *tab, int64_t *out, int64_t cap_values, int *launches, int *grid);
+/* Diagnostics: bandwidth [GB/s, read + write] of the library's own 128-bit copy loop ping-ponging between two
+ * buffers of `bytes` each, `iters` round trips -- with 2 * bytes below the L2 size this is the L2-resident roof
+ * the in-solve streaming phase runs under, above it the HBM roof (bench.py reports both beside roofline.frac). */
+int jslp_debug_copy_gbs(jslp_ctx *ctx, int64_t bytes, int iters, double *gbs);
 
 /* Tableau state read by callers after simplex() (SURVEY.md 8b "State contract"). */
 typedef struct {

@@ -68,6 +68,7 @@ SYMBOLS = [
     ("jslp_tab_upload", C.c_int, [P, P, P, P, P, C.c_int, P, C.c_int, C.c_int, P]),
     ("jslp_tab_set_option", C.c_int, [P, C.c_int, C.c_double]),
     ("jslp_debug_timeline", C.c_int, [P, P, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("jslp_debug_copy_gbs", C.c_int, [P, C.c_int64, C.c_int, C.POINTER(C.c_double)]),
     ("jslp_simplex", C.c_int, [P, C.c_int, C.POINTER(LpStatus)]),
     ("jslp_phase1", C.c_int, [P, C.c_int, C.POINTER(LpStatus)]),
     ("jslp_phase2", C.c_int, [P, C.c_int, C.POINTER(LpStatus)]),
@@ -113,6 +114,8 @@ def load(build_if_missing: bool = True):
         raise JslpError("libjslp_b200.so is missing: run `python -m jslpsolver_b200.build` (no CPU fallback)")
     L = C.CDLL(path)
     for name, res, args in SYMBOLS:
+        if os.environ.get("JSLP_LIB") and not hasattr(L, name):
+            continue  # A/B against an older build of the library: newer entry points are simply absent
         fn = getattr(L, name)  # AttributeError here == ABI drift
         fn.restype = res
         fn.argtypes = args

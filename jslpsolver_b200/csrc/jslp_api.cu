@@ -451,6 +451,66 @@ extern "C" int jslp_debug_timeline(jslp_tab *t, int64_t *out, int64_t cap_values
     return JSLP_OK;
 }
 
+namespace jslp {
+// The streaming loop of the pivot step without its arithmetic: every CTA owns one contiguous block, each thread
+// keeps 4 + 4 128-bit loads in flight (current batch + prefetched batch), like update_rows_pp.
+__global__ void __launch_bounds__(256, 2) k_copy_pairs(const double *src, double *dst, size_t n2) {
+    constexpr int K = 4;
+    const size_t per = (n2 + gridDim.x - 1) / gridDim.x;
+    const size_t lo = per * blockIdx.x, hi = lo + per < n2 ? lo + per : n2;
+    const int NT = blockDim.x;
+    double2 cur[K], nxt[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const size_t i = lo + threadIdx.x + (size_t)j * NT;
+        if (i < hi) cur[j] = ld_v2(src + 2 * i);
+    }
+    for (size_t i0 = lo + threadIdx.x; i0 < hi; i0 += (size_t)K * NT) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const size_t i = i0 + (size_t)(K + j) * NT;
+            if (i < hi) nxt[j] = ld_v2(src + 2 * i);
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const size_t i = i0 + (size_t)j * NT;
+            if (i < hi) st_v2(dst + 2 * i, cur[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) cur[j] = nxt[j];
+    }
+}
+}  // namespace jslp
+
+extern "C" int jslp_debug_copy_gbs(jslp_ctx *ctx, int64_t bytes, int iters, double *gbs) {
+    if (!ctx || !gbs || bytes < 16 || iters < 1) return fail(JSLP_E_INVALID, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    double *a = nullptr, *b = nullptr;
+    const size_t n2 = (size_t)bytes / 16;
+    CK(cudaMalloc(&a, n2 * 16));
+    CK(cudaMalloc(&b, n2 * 16));
+    CK(cudaMemsetAsync(a, 0, n2 * 16, s));
+    CK(cudaMemsetAsync(b, 0, n2 * 16, s));
+    const int grid = ctx->num_sms * 2;
+    for (int i = 0; i < 3; i++) {  // warm-up: both buffers settle where they will live
+        k_copy_pairs<<<grid, 256, 0, s>>>(a, b, n2);
+        k_copy_pairs<<<grid, 256, 0, s>>>(b, a, n2);
+    }
+    CK(cudaEventRecord(ctx->ev0, s));
+    for (int i = 0; i < iters; i++) {
+        k_copy_pairs<<<grid, 256, 0, s>>>(a, b, n2);
+        k_copy_pairs<<<grid, 256, 0, s>>>(b, a, n2);
+    }
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    cudaFree(a); cudaFree(b);
+    *gbs = 2.0 * iters * 2.0 * (double)(n2 * 16) / (ms * 1e-3) / 1e9;
+    return JSLP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Instantiations of the fused step: <threads, min CTAs/SM, rows per pass, software prefetch>.
 typedef void (*step_fn_t)(TabDev *, Rec *, int, const double *, int);

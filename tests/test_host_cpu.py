@@ -172,3 +172,33 @@ def test_host_rounding_matches_the_oracle(tmp_path):
         same = lambda got, want: got == bits(float(want)) or (want == 0 and got in (0, 1 << 63))
         assert same(int(out[2 * k], 16), want_r), (x, "round")
         assert same(int(out[2 * k + 1], 16), want_e), (x, p, "evaluation")
+
+
+def test_napi_addon_compiles_against_the_header(tmp_path):
+    """binding/jslp_addon.cc (the N-API shim of north_star) is compiled -- -Wall -Wextra -Werror -- against the real
+    include/jslp_b200.h and a stub node_api.h that carries Node's own prototypes for the N-API calls it makes; every
+    jslp_* symbol the object file needs must be exported by libjslp_b200.so, every napi_* one declared by the stub."""
+    import re
+    import subprocess
+    from jslpsolver_b200 import _lib
+    obj = tmp_path / "jslp_addon.o"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-fPIC", "-c", "-I", os.path.join(ROOT, "tests", "stubs"),
+                    "-I", os.path.join(ROOT, "include"), "-o", str(obj), os.path.join(ROOT, "binding", "jslp_addon.cc")], check=True)
+    undef = subprocess.run(["nm", "-u", str(obj)], check=True, capture_output=True, text=True).stdout.split()
+    need_jslp = {s for s in undef if s.startswith("jslp_")}
+    need_napi = {s for s in undef if s.startswith("napi_")}
+    assert len(need_jslp) >= 20 and len(need_napi) >= 30
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert need_jslp <= bound, need_jslp - bound
+    L = _lib.load(build_if_missing=False)
+    for s in need_jslp:
+        assert hasattr(L, s), s
+    stub = open(os.path.join(ROOT, "tests", "stubs", "node_api.h")).read()
+    declared = set(re.findall(r"\b(napi_[a-z0-9_]+)\s*\(", stub))
+    assert need_napi <= declared, need_napi - declared
+    # the TypeScript glue names the same addon methods the shim defines
+    ts = open(os.path.join(ROOT, "binding", "src", "tableau", "gpu-tableau.ts")).read()
+    cc = open(os.path.join(ROOT, "binding", "jslp_addon.cc")).read()
+    methods = set(re.findall(r'\{"([A-Za-z0-9]+)", nullptr, tab_', cc))
+    used = set(re.findall(r"this\.tab\(\)\.([A-Za-z0-9]+)\(", ts))
+    assert used and used <= methods, used - methods
