@@ -88,7 +88,9 @@ enum {
     JSLP_OPT_NODE_SLOTS = 10,  /* node LPs in flight side by side in HBM: -1 = auto (default), 0 = one at a
                                   time (the reference's literal applyCuts sequence), n = at most n slots */
     JSLP_OPT_SLOT_STEPS = 11,  /* pivots per slot between host polls of the slot batch (default 32)   */
-    JSLP_OPT_SLOT_VARIANT = 12 /* kernel instantiation used by the slot batch (JSLP_OPT_STEP_VARIANT values) */
+    JSLP_OPT_SLOT_VARIANT = 12, /* kernel instantiation used by the slot batch (JSLP_OPT_STEP_VARIANT values) */
+    JSLP_OPT_USE_MIR_CUTS = 13  /* model.useMIRCuts (model.ts:69,313): applyCuts / branchAndCut run the MIR loop of
+                                   branch-and-cut.ts:38-51 after every node's simplex()                          */
 };
 int jslp_tab_set_option(jslp_tab *tab, int key, double value);
 /* Diagnostics: per-CTA timeline (8 int64 per CTA per launch) recorded under JSLP_OPT_TIMELINE. */
@@ -140,7 +142,13 @@ typedef struct {
 
 /* == Tableau.addCutConstraints(cuts) (cutting-strategies.ts:16-72). */
 int jslp_add_cuts(jslp_tab *tab, const jslp_cut *cuts, int n);
-/* == BranchAndCutService.applyCuts (branch-and-cut.ts:33-52): restore, add cuts, simplex. */
+/* == Tableau.addLowerBoundMIRCut(row) (upper_bound = 0) / addUpperBoundMIRCut(row) (1), cutting-strategies.ts:
+ * 74-196: *added = 1 when a cut row (and its slack) was appended.  == Tableau.applyMIRCuts() (198-212): lower-
+ * bound cuts on the first (at most 10) eligible rows.  == Tableau.computeFractionalVolume (mip-utils.ts:67-98). */
+int jslp_add_mir_cut(jslp_tab *tab, int row, int upper_bound, int *added);
+int jslp_apply_mir_cuts(jslp_tab *tab, int *n_added);
+int jslp_fractional_volume(jslp_tab *tab, int ignore_integer_values, double *volume);
+/* == BranchAndCutService.applyCuts (branch-and-cut.ts:33-52): restore, add cuts, simplex [, MIR loop]. */
 int jslp_apply_cuts(jslp_tab *tab, const jslp_cut *cuts, int n, int check_cycles, jslp_lp_status *out);
 /* == Tableau.isIntegral() (mip-utils.ts:43-61) and getMostFractionalVar() (mip-utils.ts:100-126):
  * *var_index = -1 when no fractional integer variable exists.                             */

@@ -11,7 +11,7 @@ _LIB = None
 
 OPT_ENGINE, OPT_BATCH, OPT_PIVOT_LOG_CAP = 1, 2, 3
 OPT_STEP_VARIANT, OPT_GRID_PER_SM, OPT_LOOKAHEAD, OPT_TIMELINE, OPT_PDL, OPT_PINGPONG = 4, 5, 6, 7, 8, 9
-OPT_NODE_SLOTS, OPT_SLOT_STEPS, OPT_SLOT_VARIANT = 10, 11, 12
+OPT_NODE_SLOTS, OPT_SLOT_STEPS, OPT_SLOT_VARIANT, OPT_USE_MIR_CUTS = 10, 11, 12, 13
 ENGINE_AUTO, ENGINE_TWO_KERNEL, ENGINE_FUSED, ENGINE_PERSISTENT, ENGINE_RESIDENT = 0, 1, 2, 3, 4
 
 
@@ -77,6 +77,9 @@ SYMBOLS = [
     ("jslp_restore", C.c_int, [P]),
     ("jslp_add_cuts", C.c_int, [P, P, C.c_int]),
     ("jslp_apply_cuts", C.c_int, [P, P, C.c_int, C.c_int, C.POINTER(LpStatus)]),
+    ("jslp_add_mir_cut", C.c_int, [P, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("jslp_apply_mir_cuts", C.c_int, [P, C.POINTER(C.c_int)]),
+    ("jslp_fractional_volume", C.c_int, [P, C.c_int, C.POINTER(C.c_double)]),
     ("jslp_is_integral", C.c_int, [P, C.POINTER(C.c_int)]),
     ("jslp_most_fractional", C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     ("jslp_download", C.c_int, [P, P, P, P, P, P, P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -157,6 +157,9 @@ struct jslp_tab {
     double slot_ms = 0, slot_bytes = 0;
     ResidentBufs rbufs;
     NodeSlots slots;        // K3: HBM-resident node batch (jslp_slots.cuh)
+    int use_mir = 0;        // model.useMIRCuts (JSLP_OPT_USE_MIR_CUTS)
+    std::vector<int> h_intpos;  // host copy of TabDev.intpos (computeFractionalVolume runs on the host)
+    int *d_count = nullptr, *h_count = nullptr;
     int node_slots = -1;    // JSLP_OPT_NODE_SLOTS: -1 = auto, 0 = off (one node at a time), n = at most n slots
     int slot_steps = 32;    // pivots per slot per host poll
     int slot_variant = 11;  // kernel instantiation of the slot batch (flat streaming: the batch is HBM-bound)
@@ -284,6 +287,8 @@ extern "C" int jslp_tab_create(jslp_ctx *ctx, int width, int height, int row_cap
     CK(cudaEventCreateWithFlags(&t->ev_slot[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&t->ev_slot[1], cudaEventDisableTiming));
     CK(cudaMallocHost(&t->h_mip, sizeof(MipOut)));
+    CK(cudaMalloc(&t->d_count, sizeof(int)));
+    CK(cudaMallocHost(&t->h_count, sizeof(int)));
     CK(cudaMemsetAsync(t->d_rec, 0, sizeof(Rec), ctx->stream));
     CK(cudaMemsetAsync(t->hd.prow, 0, sizeof(double) * (size_t)t->stride, ctx->stream));
     // phase-2 partial pricing parameters (simplex.ts:118-127)
@@ -319,6 +324,7 @@ extern "C" void jslp_tab_destroy(jslp_tab *t) {
     cudaFree(t->hd.part); cudaFree(t->hd.dbg); cudaFree(t->hd.M2); cudaFree(t->hd.crow);
     cudaFree(t->d_T); cudaFree(t->d_rec); cudaFree(t->d_mip); cudaFree(t->d_cuts);
     cudaFreeHost(t->h_rec); cudaFreeHost(t->h_log); cudaFreeHost(t->h_mip); cudaFreeHost(t->h_cuts);
+    cudaFree(t->d_count); cudaFreeHost(t->h_count);
     free_saved(t->saved);
     free_snap(t->snaps[0]);
     free_snap(t->snaps[1]);
@@ -349,6 +355,7 @@ extern "C" int jslp_tab_upload(jslp_tab *t, const double *matrix, const int32_t 
         CK(cudaMemcpyAsync(t->hd.unres, unrestricted, (size_t)t->n_index, cudaMemcpyHostToDevice, s));
     }
     cudaFree(t->hd.intpos); t->hd.intpos = nullptr;
+    t->h_intpos.clear();
     t->n_int = n_int;
     if (n_int > 0) {
         if (!int_vars) return fail(JSLP_E_INVALID, "int_var_indices is NULL");
@@ -357,6 +364,7 @@ extern "C" int jslp_tab_upload(jslp_tab *t, const double *matrix, const int32_t 
             if (int_vars[i] < 0 || int_vars[i] >= t->n_index) return fail(JSLP_E_INVALID, "integer var index out of range");
             if (pos[int_vars[i]] < 0) pos[int_vars[i]] = i;
         }
+        t->h_intpos = pos;
         CK(cudaMalloc(&t->hd.intpos, sizeof(int) * (size_t)t->n_index));
         CK(cudaMemcpyAsync(t->hd.intpos, pos.data(), sizeof(int) * (size_t)t->n_index, cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
@@ -419,6 +427,9 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
         case JSLP_OPT_NODE_SLOTS:
             if (value < -1 || value > 64) return fail(JSLP_E_INVALID, "node slots must be -1..64");
             t->node_slots = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_USE_MIR_CUTS:
+            t->use_mir = value != 0;
             return JSLP_OK;
         case JSLP_OPT_SLOT_VARIANT:
             if (value < 0 || value >= n_step_variants()) return fail(JSLP_E_INVALID, "slot variant out of range");
@@ -1126,12 +1137,109 @@ extern "C" int jslp_add_cuts(jslp_tab *t, const jslp_cut *cuts, int n) {
     return JSLP_OK;
 }
 
+// addLowerBoundMIRCut / addUpperBoundMIRCut (row >= 0) and applyMIRCuts (row < 0), cutting-strategies.ts:74-212
+static int mir_cuts(jslp_tab *t, int row, int upper, int *n_added) {
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    const int max_cuts = 10;  // cutting-strategies.ts:203
+    const int grid_before = step_grid(t);
+    int rc = grow_rows(t, t->H + (row >= 0 ? 1 : max_cuts));
+    if (rc) return rc;
+    rc = push_desc(t);
+    if (rc) return rc;
+    k_mir_cuts<<<1, 256, 0, s>>>(t->d_T, t->H, t->lastElementIndex, row, upper, max_cuts, t->d_count);
+    t->ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(t->h_count, t->d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n = *t->h_count;
+    t->H += n;
+    t->nVars += n;             // cutting-strategies.ts:106 / 168
+    t->lastElementIndex += n;  // getNewElementIndex (tableau.ts:393-401)
+    if (n_added) *n_added = n;
+    if (n > 0) {
+        rc = push_desc(t);
+        if (rc) return rc;
+    }
+    if (step_grid(t) != grid_before) drop_graphs(t);
+    return JSLP_OK;
+}
+
+extern "C" int jslp_add_mir_cut(jslp_tab *t, int row, int upper_bound, int *added) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    if (row < 0 || row >= t->H) { if (added) *added = 0; return JSLP_OK; }
+    return mir_cuts(t, row, upper_bound != 0, added);
+}
+extern "C" int jslp_apply_mir_cuts(jslp_tab *t, int *n_added) {
+    if (!t) return fail(JSLP_E_INVALID, "tab is NULL");
+    return mir_cuts(t, -1, 0, n_added);
+}
+
+// computeFractionalVolume (mip-utils.ts:67-98): a product over the basic integer variables in row order --
+// an order-dependent fp64 product, so it is evaluated on the host over the downloaded right-hand-side column.
+extern "C" int jslp_fractional_volume(jslp_tab *t, int ignore_integer_values, double *volume) {
+    if (!t || !volume) return fail(JSLP_E_INVALID, "NULL argument");
+    std::vector<double> rhs((size_t)t->H);
+    std::vector<int> vrow((size_t)t->H);
+    int rc = jslp_download(t, nullptr, rhs.data(), nullptr, vrow.data(), nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    double vol = -1;
+    for (int r = 1; r < t->H; r++) {
+        const int v = vrow[r];
+        if (v < 0 || v >= (int)t->h_intpos.size() || t->h_intpos[v] < 0) continue;
+        const double distance = std::fabs(rhs[r]);
+        const double a = distance - std::floor(distance), b = std::floor(distance + 1);
+        if ((a < b ? a : b) < t->precision) {
+            if (!ignore_integer_values) { *volume = 0; return JSLP_OK; }
+        } else if (vol == -1) {
+            vol = distance;
+        } else {
+            vol *= distance;
+        }
+    }
+    *volume = vol == -1 ? 0 : vol;
+    return JSLP_OK;
+}
+
+// simplex() followed, under model.useMIRCuts, by the loop of branch-and-cut.ts:38-51.  Reports how many of the
+// simplex() calls ended optimal and the evaluation of the first one (Tableau.simplexIters / bestPossibleEval).
+static int simplex_with_mir(jslp_tab *t, int check_cycles, jslp_lp_status *out, bool timed, int *n_optimal, double *first_eval) {
+    const int it0 = t->simplexIters;
+    int rc = run_lp(t, 0, check_cycles, out, timed);
+    if (rc) return rc;
+    bool have_first = t->simplexIters != it0;
+    double first = t->evaluation;
+    int p1 = out ? out->phase1_pivots : 0, p2 = out ? out->phase2_pivots : 0;
+    if (t->use_mir) {
+        bool improved = true;
+        while (improved) {
+            double before = 0, after = 0;
+            rc = jslp_fractional_volume(t, 1, &before);
+            if (rc) return rc;
+            rc = mir_cuts(t, -1, 0, nullptr);
+            if (rc) return rc;
+            const int it1 = t->simplexIters;
+            rc = run_lp(t, 0, check_cycles, out, false);
+            if (rc) return rc;
+            if (!have_first && t->simplexIters != it1) { have_first = true; first = t->evaluation; }
+            if (out) { p1 += out->phase1_pivots; p2 += out->phase2_pivots; }
+            rc = jslp_fractional_volume(t, 1, &after);
+            if (rc) return rc;
+            if (after >= 0.9 * before) improved = false;
+        }
+        if (out) { out->phase1_pivots = p1; out->phase2_pivots = p2; }
+    }
+    if (n_optimal) *n_optimal = t->simplexIters - it0;
+    if (first_eval) *first_eval = first;
+    return JSLP_OK;
+}
+
 extern "C" int jslp_apply_cuts(jslp_tab *t, const jslp_cut *cuts, int n, int check_cycles, jslp_lp_status *out) {
     int rc = jslp_restore(t);
     if (rc) return rc;
     rc = jslp_add_cuts(t, cuts, n);
     if (rc) return rc;
-    return run_lp(t, 0, check_cycles, out, true);
+    return simplex_with_mir(t, check_cycles, out, true, nullptr, nullptr);
 }
 
 static int mip_scan(jslp_tab *t, MipOut *o) {

@@ -37,11 +37,15 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
     const auto t_2 = tnow();
     const double prevBest = t->bestPossibleEval;
     const int prevIters = t->simplexIters;
-    rc = run_lp(t, 0, check_cycles, &st, false);
+    int n_optimal = 0;
+    double first_eval = 0;
+    rc = simplex_with_mir(t, check_cycles, &st, false, &n_optimal, &first_eval);
     if (rc) return rc;
     const auto t_3 = tnow();
     // simplexIters / bestPossibleEval are frontier state: the commit loop owns them
-    ev.optimal = t->simplexIters != prevIters;
+    ev.optimal = n_optimal > 0;
+    ev.n_optimal = t->use_mir ? n_optimal : -1;
+    ev.first_eval = first_eval;
     t->simplexIters = prevIters;
     t->bestPossibleEval = prevBest;
     ev.valid = true;
@@ -497,8 +501,8 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         t->feasible = ev.feasible; t->bounded = ev.bounded;
         if (ev.feasible) t->evaluation = ev.evaluation;
         if (ev.optimal) {  // setEvaluation + simplexIters (tableau.ts:420-430, simplex.ts:266-267)
-            if (t->simplexIters == 0) t->bestPossibleEval = ev.evaluation;
-            t->simplexIters += 1;
+            if (t->simplexIters == 0) t->bestPossibleEval = ev.n_optimal >= 0 ? ev.first_eval : ev.evaluation;
+            t->simplexIters += ev.n_optimal >= 0 ? ev.n_optimal : 1;
         }
         NodeLogEntry nl;
         nl.v[0] = iterations; nl.v[1] = (double)active->cuts.size(); nl.v[2] = ev.feasible;
@@ -587,14 +591,15 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             int maxc_all = 0;
             for (Branch *b : todo) maxc_all = std::max(maxc_all, (int)b->cuts.size());
             // every rank takes the same decisions from the same (rank-independent) quantities
-            const bool resident = iterations > 0 && t->saved.valid && t->engine != 1 && t->engine != 2 &&
+            // useMIRCuts: the MIR loop (fractional volume, cut rows, re-solves) runs on the single-tableau path
+            const bool resident = iterations > 0 && t->saved.valid && t->engine != 1 && t->engine != 2 && !t->use_mir &&
                                   resident_fits(t, t->saved.H + maxc_all);
-            const int nslots = (!resident && iterations > 0 && t->saved.valid && todo.size() >= 2)
+            const int nslots = (!resident && !t->use_mir && iterations > 0 && t->saved.valid && todo.size() >= 2)
                                    ? slots_for(t, t->saved.H + maxc_all, std::max(K, (int)todo.size())) : 0;
             // The root round is NOT sharded: every rank needs the solved root in its own tableau, it is what
             // jslp_save snapshots and what every later node is derived from.  Rounds of nodes that fit shared
             // memory are not sharded either unless asked: a whole round costs less than one collective.
-            const bool sharded = n_ranks > 1 && iterations > 0 && (opts->shard_policy == 1 || !resident);
+            const bool sharded = n_ranks > 1 && iterations > 0 && !t->use_mir && (opts->shard_policy == 1 || !resident);
             std::vector<Branch *> mine;
             for (size_t i = 0; i < todo.size(); i++)
                 if (!sharded || (int)(i % n_ranks) == rank) mine.push_back(todo[i]);
@@ -675,7 +680,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
             nodes++;
             if (bestBranch) {
                 pivots += ev.pivots;
-                if (ev.optimal) t->simplexIters += 1;
+                if (ev.optimal) t->simplexIters += ev.n_optimal >= 0 ? ev.n_optimal : 1;
             }
             final_ms = ms_since(t_fin);
         }

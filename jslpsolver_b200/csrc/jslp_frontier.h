@@ -18,6 +18,10 @@ struct NodeEval {  // what the commit loop needs from one node LP
     bool valid = false;
     int feasible = 0, bounded = 1, optimal = 0, is_integral = 0, branch_var = -1, pivots = 0;
     double evaluation = 0, branch_value = 0;
+    // useMIRCuts only (never on the wire: such models are not sharded): simplex() calls of this node that ended
+    // optimal (Tableau.simplexIters) and the evaluation of the first one (Tableau.bestPossibleEval at the root)
+    int n_optimal = -1;  // -1 = one solve: use `optimal`
+    double first_eval = 0;
     double opt0[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // optionalObjectives[o].reducedCosts[0]
 };
 

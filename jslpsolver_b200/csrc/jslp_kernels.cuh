@@ -801,6 +801,88 @@ __global__ void __launch_bounds__(256) k_add_cuts(const TabDev *Tp, const CutDev
     if (tid == 0) T.vrow[H0 + h] = first_index + h;
 }
 
+// Math.max(0, x) / Math.min(0, y) with JS semantics (NaN propagates; max(0, -0) = +0; min(0, -0) = -0)
+__device__ __forceinline__ double js_max0(double x) { return x != x ? x : (x > 0 ? x : 0.0); }
+__device__ __forceinline__ double js_min0(double y) { return y != y ? y : (y < 0 ? y : ((y == 0 && signbit(y)) ? y : 0.0)); }
+
+// addLowerBoundMIRCut / addUpperBoundMIRCut / applyMIRCuts (cutting-strategies.ts:74-212), one CTA.
+// row >= 0: try exactly that row (upper = 0 / 1); row < 0: applyMIRCuts -- rows 1 .. H0-1 in ascending order,
+// lower-bound cut on each row whose basic variable is integer with a fractional right-hand side, at most
+// max_cuts.  Cut k becomes row H0 + k with slack index first_index + k; *n_added = number of rows appended.
+__global__ void __launch_bounds__(256) k_mir_cuts(const TabDev *Tp, int H0, int first_index, int row, int upper, int max_cuts,
+                                                  int *n_added) {
+    __shared__ int s_flag[256];
+    __shared__ int s_rows[16];
+    __shared__ int s_n;
+    const TabDev &T = *Tp;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const size_t stride = (size_t)T.stride;
+    const double prec = T.prec;
+    auto is_int = [&](int v) { return T.intpos != nullptr && v >= 0 && v < T.n_index && T.intpos[v] >= 0; };
+    auto eligible = [&](int r) {
+        if (r <= 0 || r >= H0) return false;                       // costRowIndex / out of range
+        if (!is_int(T.vrow[r])) return false;                      // integerVar undefined or not integer
+        const double rhs = T.M[r * stride];
+        const double frac = rhs - floor(rhs);
+        return !(frac < prec || frac > 1 - prec);
+    };
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if (row >= 0) {
+        if (tid == 0 && eligible(row)) { s_rows[0] = row; s_n = 1; }
+        __syncthreads();
+    } else {
+        if (max_cuts > 16) max_cuts = 16;
+        for (int base = 1; base < H0; base += NT) {
+            s_flag[tid] = eligible(base + tid) ? 1 : 0;
+            __syncthreads();
+            if (tid == 0)
+                for (int k = 0; k < NT && s_n < max_cuts; k++)
+                    if (s_flag[k]) s_rows[s_n++] = base + k;
+            __syncthreads();
+            if (s_n >= max_cuts) break;
+        }
+    }
+    const int n = s_n;
+    for (int k = 0; k < n; k++) {
+        const int r = s_rows[k];
+        const double *src = T.M + r * stride;
+        double *nw = T.M + (size_t)(H0 + k) * stride;
+        const double rhs = src[0];
+        const double frac = rhs - floor(rhs);
+        for (int c = tid; c < T.stride; c += NT) {
+            double v = 0.0;
+            if (c < T.W) {
+                const double coefficient = src[c];
+                if (!upper) {
+                    if (c == 0) v = floor(rhs);
+                    else if (is_int(T.vcol[c])) {
+                        const double fl = floor(coefficient);
+                        const double a = __dsub_rn(coefficient, fl);
+                        const double b = __dsub_rn(a, frac);
+                        v = __dadd_rn(fl, ddiv(js_max0(b), __dsub_rn(1.0, frac)));
+                    } else {
+                        v = js_min0(ddiv(coefficient, __dsub_rn(1.0, frac)));
+                    }
+                    v = __dsub_rn(v, coefficient);  // cutting-strategies.ts:129-131
+                } else {
+                    if (c == 0) v = -frac;
+                    else {
+                        const double termCoeff = __dsub_rn(coefficient, floor(coefficient));
+                        if (is_int(T.vcol[c]))
+                            v = termCoeff <= frac ? -termCoeff : ddiv(__dmul_rn(-__dsub_rn(1.0, termCoeff), frac), termCoeff);
+                        else
+                            v = coefficient >= 0 ? -coefficient : ddiv(__dmul_rn(coefficient, frac), __dsub_rn(1.0, frac));
+                    }
+                }
+            }
+            nw[c] = v;
+        }
+        if (tid == 0) T.vrow[H0 + k] = first_index + k;
+    }
+    if (tid == 0) *n_added = n;
+}
+
 // isIntegral + getMostFractionalVar (mip-utils.ts:43-61,100-126) over the RHS column.
 __device__ __forceinline__ void cta_mip_scan(const TabDev &T, MipOut *out, RedSmem &red) {
     const VI init = {0.0, INT_MAX};

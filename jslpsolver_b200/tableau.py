@@ -272,12 +272,36 @@ class GpuTableau:
         _lib.check(self.context.lib.jslp_add_cuts(self._h(), self._cut_array(branchingCuts), len(branchingCuts)))
         self._refresh_dims()
 
+    def addLowerBoundMIRCut(self, rowIndex: int) -> bool:   # cutting-strategies.ts:74-134
+        a = C.c_int()
+        _lib.check(self.context.lib.jslp_add_mir_cut(self._h(), int(rowIndex), 0, C.byref(a)))
+        self._refresh_dims()
+        return bool(a.value)
+
+    def addUpperBoundMIRCut(self, rowIndex: int) -> bool:   # cutting-strategies.ts:136-196
+        a = C.c_int()
+        _lib.check(self.context.lib.jslp_add_mir_cut(self._h(), int(rowIndex), 1, C.byref(a)))
+        self._refresh_dims()
+        return bool(a.value)
+
+    def applyMIRCuts(self) -> None:                         # cutting-strategies.ts:198-212
+        n = C.c_int()
+        _lib.check(self.context.lib.jslp_apply_mir_cuts(self._h(), C.byref(n)))
+        self._refresh_dims()
+
+    def computeFractionalVolume(self, ignoreIntegerValues: bool = False) -> float:  # mip-utils.ts:67-98
+        v = C.c_double()
+        _lib.check(self.context.lib.jslp_fractional_volume(self._h(), int(bool(ignoreIntegerValues)), C.byref(v)))
+        return v.value
+
+    def _sync_mir_option(self) -> None:
+        self.set_option(_lib.OPT_USE_MIR_CUTS, 1 if getattr(self.model, "useMIRCuts", False) else 0)
+
     def applyCuts(self, branchingCuts) -> None:
         if self.branchAndCutService is not None:
             self.branchAndCutService.applyCuts(self, branchingCuts)
             return
-        if getattr(self.model, "useMIRCuts", False):
-            raise JslpError("useMIRCuts is outside the GPU hot-path scope (SURVEY.md 8f.3)")
+        self._sync_mir_option()
         st = LpStatus()
         _lib.check(self.context.lib.jslp_apply_cuts(self._h(), self._cut_array(branchingCuts), len(branchingCuts),
                                                     self._check_cycles(), C.byref(st)))
@@ -298,8 +322,7 @@ class GpuTableau:
             self.branchAndCutService.branchAndCut(self)
             return
         m = self.model
-        if getattr(m, "useMIRCuts", False):
-            raise JslpError("useMIRCuts is outside the GPU hot-path scope (SURVEY.md 8f.3)")
+        self._sync_mir_option()
         opts = BnbOpts()
         opts.tolerance = float(getattr(m, "tolerance", 0) or 0)
         opts.is_minimization = int(bool(getattr(m, "isMinimization", True)))

@@ -15,6 +15,8 @@
  *   tableau.ts:420-430  setEvaluation      -> set_evaluation
  *   backup.ts:13-105    copy/save/restore  -> orc_save / orc_restore
  *   cutting-strategies.ts:16-72 addCutConstraints -> orc_add_cuts
+ *   cutting-strategies.ts:74-212 addLowerBoundMIRCut / addUpperBoundMIRCut / applyMIRCuts -> orc_add_mir_cut / orc_apply_mir_cuts
+ *   mip-utils.ts:67-98  computeFractionalVolume -> orc_fractional_volume
  *   mip-utils.ts:43-61,100-126  isIntegral / getMostFractionalVar
  *   min-heap.ts:18-119  BranchMinHeap      -> heap_push / heap_pop
  *   branch-and-cut.ts:33-199    applyCuts / branchAndCut -> apply_cuts / orc_branch_and_cut
@@ -93,6 +95,7 @@ typedef struct orc_tab {
     double *nlog;
     long nlogCap, nlogN;
     long maxNodes; /* safety cap, 0 = none */
+    int useMIR;    /* model.useMIRCuts */
     /* best cuts of the winning branch (for tests) */
     orc_cut *bestCuts;
     int nBestCuts;
@@ -196,6 +199,8 @@ void orc_set_options(orc_tab *t, int checkCycles, int fastCycles, int isMin, dou
     t->checkCycles = checkCycles; t->fastCycles = fastCycles; t->isMin = isMin;
     t->tolerance = tolerance; t->maxNodes = maxNodes;
 }
+
+void orc_set_use_mir(orc_tab *t, int useMIR) { t->useMIR = useMIR; }
 
 void orc_enable_pivot_log(orc_tab *t, long cap) {
     free(t->plog);
@@ -600,6 +605,95 @@ void orc_add_cuts(orc_tab *t, const orc_cut *cuts, int n) {
     }
 }
 
+static int var_is_integer(const orc_tab *t, int varIndex) {
+    for (int v = 0; v < t->nInt; v++)
+        if (t->intVars[v] == varIndex) return 1;
+    return 0;
+}
+
+/* Math.max(0, x) / Math.min(0, y) with JS semantics (NaN propagates; max(0,-0) = +0; min(0,-0) = -0) */
+static double js_max0(double x) { return x != x ? x : (x > 0 ? x : 0.0); }
+static double js_min0(double y) { return y != y ? y : (y < 0 ? y : (y == 0 && signbit(y) ? y : 0.0)); }
+
+/* cutting-strategies.ts:74-134 (upper == 0) and 136-196 (upper != 0); returns 1 when a cut row was added */
+int orc_add_mir_cut(orc_tab *t, int rowIndex, int upper) {
+    if (rowIndex == 0) return 0;  /* costRowIndex */
+    if (rowIndex < 0 || rowIndex >= t->H) return 0;
+    const int W = t->W;
+    if (!var_is_integer(t, t->vrow[rowIndex])) return 0;  /* integerVar undefined or not integer */
+    const double rhsValue = t->M[(size_t)rowIndex * W];
+    const double fractionalPart = rhsValue - floor(rhsValue);
+    if (fractionalPart < t->precision || fractionalPart > 1 - t->precision) return 0;
+    const int height = t->H;
+    ensure_rows(t, height + 1);
+    double *mat = t->M;
+    const double *src = mat + (size_t)rowIndex * W;
+    double *nw = mat + (size_t)height * W;
+    t->H += 1;
+    t->nVars += 1;
+    const int slackVarIndex = new_element_index(t);
+    ensure_maps(t, slackVarIndex + 1);
+    t->vrow[height] = slackVarIndex;
+    t->rowOf[slackVarIndex] = height;
+    t->colOf[slackVarIndex] = -1;
+    if (!upper) {
+        nw[0] = floor(rhsValue);
+        for (int c = 1; c < W; c++) {
+            const double coefficient = src[c];
+            if (var_is_integer(t, t->vcol[c])) {
+                const double fl = floor(coefficient);
+                const double a = coefficient - fl;
+                const double b = a - fractionalPart;
+                nw[c] = fl + js_max0(b) / (1 - fractionalPart);
+            } else {
+                nw[c] = js_min0(coefficient / (1 - fractionalPart));
+            }
+        }
+        for (int c = 0; c < W; c++) nw[c] -= src[c];
+    } else {
+        nw[0] = -fractionalPart;
+        for (int c = 1; c < W; c++) {
+            const double coefficient = src[c];
+            const double termCoeff = coefficient - floor(coefficient);
+            if (var_is_integer(t, t->vcol[c])) {
+                nw[c] = termCoeff <= fractionalPart ? -termCoeff : (-(1 - termCoeff) * fractionalPart) / termCoeff;
+            } else {
+                nw[c] = coefficient >= 0 ? -coefficient : (coefficient * fractionalPart) / (1 - fractionalPart);
+            }
+        }
+    }
+    return 1;
+}
+
+/* cutting-strategies.ts:198-212; returns the number of cuts added */
+int orc_apply_mir_cuts(orc_tab *t) {
+    const int height = t->H;
+    int cutsAdded = 0;
+    const int maxCuts = 10;
+    for (int r = 1; r < height && cutsAdded < maxCuts; r++)
+        if (orc_add_mir_cut(t, r, 0)) cutsAdded++;
+    return cutsAdded;
+}
+
+/* mip-utils.ts:67-98 */
+double orc_fractional_volume(const orc_tab *t, int ignoreIntegerValues) {
+    double volume = -1;
+    for (int r = 1; r < t->H; r++) {
+        if (!var_is_integer(t, t->vrow[r])) continue;
+        const double value = t->M[(size_t)r * t->W];
+        const double distance = fabs(value);
+        const double a = distance - floor(distance), b = floor(distance + 1);
+        if ((a < b ? a : b) < t->precision) {  /* Math.min of two non-NaN numbers */
+            if (!ignoreIntegerValues) return 0;
+        } else if (volume == -1) {
+            volume = distance;
+        } else {
+            volume *= distance;
+        }
+    }
+    return volume == -1 ? 0 : volume;
+}
+
 /* mip-utils.ts:43-61 */
 int orc_is_integral(const orc_tab *t) {
     for (int v = 0; v < t->nInt; v++) {
@@ -683,11 +777,21 @@ static orc_branch *make_branch(double ev, int nCuts) {
 }
 static void free_branch(orc_branch *b) { if (b) { free(b->cuts); free(b); } }
 
-/* branch-and-cut.ts:33-52 (useMIRCuts is out of scope: SURVEY 8f.3) */
+/* branch-and-cut.ts:33-52 */
 static void apply_cuts(orc_tab *t, const orc_cut *cuts, int n) {
     orc_restore(t);
     orc_add_cuts(t, cuts, n);
     orc_simplex(t);
+    if (t->useMIR) {
+        int fractionalVolumeImproved = 1;
+        while (fractionalVolumeImproved) {
+            const double fractionalVolumeBefore = orc_fractional_volume(t, 1);
+            orc_apply_mir_cuts(t);
+            orc_simplex(t);
+            const double fractionalVolumeAfter = orc_fractional_volume(t, 1);
+            if (fractionalVolumeAfter >= 0.9 * fractionalVolumeBefore) fractionalVolumeImproved = 0;
+        }
+    }
 }
 
 void orc_apply_cuts(orc_tab *t, const orc_cut *cuts, int n) { apply_cuts(t, cuts, n); }

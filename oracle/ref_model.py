@@ -92,6 +92,13 @@ def lib():
         L.orc_row_of.restype = ctypes.c_int
         L.orc_set_flags.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.orc_set_pivot_limit.argtypes = [ctypes.c_void_p, ctypes.c_long]
+        L.orc_set_use_mir.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_add_mir_cut.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.orc_add_mir_cut.restype = ctypes.c_int
+        L.orc_apply_mir_cuts.argtypes = [ctypes.c_void_p]
+        L.orc_apply_mir_cuts.restype = ctypes.c_int
+        L.orc_fractional_volume.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_fractional_volume.restype = ctypes.c_double
         L.orc_truncated.argtypes = [ctypes.c_void_p]
         L.orc_truncated.restype = ctypes.c_int
         L.orc_cycles_ref.argtypes = [ctypes.c_void_p, ctypes.c_long,
@@ -541,7 +548,7 @@ class OracleTableau:
 
     def __init__(self, M, vrow, vcol, precision=1e-8, unrestricted=None, integers=None,
                  opt_rc=None, check_cycles=True, fast_cycles=False, is_min=True, tolerance=0.0,
-                 max_nodes=0, pivot_log=0, node_log=0):
+                 max_nodes=0, pivot_log=0, node_log=0, use_mir=False):
         L = lib()
         M = np.ascontiguousarray(M, dtype=np.float64)
         self.H0, self.W = M.shape
@@ -561,6 +568,7 @@ class OracleTableau:
         self.nOpt = 0 if opt_rc is None else len(opt_rc)
         L.orc_set_options(self.h, int(bool(check_cycles)), int(bool(fast_cycles)), int(bool(is_min)),
                           float(tolerance), int(max_nodes))
+        L.orc_set_use_mir(self.h, int(bool(use_mir)))
         if pivot_log:
             L.orc_enable_pivot_log(self.h, pivot_log)
         if node_log:
@@ -618,6 +626,15 @@ class OracleTableau:
     def branch_and_cut(self):
         lib().orc_branch_and_cut(self.h)
         return self.state()
+
+    def add_mir_cut(self, row, upper=False):   # addLowerBoundMIRCut / addUpperBoundMIRCut
+        return bool(lib().orc_add_mir_cut(self.h, int(row), int(bool(upper))))
+
+    def apply_mir_cuts(self):                  # applyMIRCuts
+        return lib().orc_apply_mir_cuts(self.h)
+
+    def fractional_volume(self, ignore_integer_values=False):  # computeFractionalVolume
+        return lib().orc_fractional_volume(self.h, int(bool(ignore_integer_values)))
 
     def is_integral(self):
         return bool(lib().orc_is_integral(self.h))
@@ -697,8 +714,6 @@ def solve_full(jm: dict, precision=None, fast_cycles=False, pivot_log=0, node_lo
     model = RefModel(precision).loadJson(jm)
     sol = OracleSolution()
     sol.model = model
-    if model.useMIRCuts:
-        raise NotImplementedError("useMIRCuts is outside the hot-path scope (SURVEY 8f.3)")
     if model.usePresolve:
         infeasible, fixed = presolve(model)
         if infeasible:  # model.ts:432-436
@@ -719,7 +734,7 @@ def solve_full(jm: dict, precision=None, fast_cycles=False, pivot_log=0, node_lo
     tab = OracleTableau(M, vrow, vcol, precision=model.precision, unrestricted=unres, integers=ints,
                         opt_rc=rc, check_cycles=model.checkForCycles, fast_cycles=fast_cycles,
                         is_min=model.isMinimization, tolerance=model.tolerance or 0.0,
-                        max_nodes=max_nodes, pivot_log=pivot_log, node_log=node_log)
+                        max_nodes=max_nodes, pivot_log=pivot_log, node_log=node_log, use_mir=bool(model.useMIRCuts))
     sol.tableau = tab
     if ints:  # tableau.ts:250-258
         st = tab.branch_and_cut()

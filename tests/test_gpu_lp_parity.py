@@ -345,3 +345,55 @@ def test_keep_solutions_stores_every_incumbent():
             final = {k: v for k, v in gsol.solutionSet.items()}
             assert last == final, name
         assert s._simplified(gsol) == ref_model.Solve(jm, fast_cycles=True)
+
+
+# ------------------------------------------------------------------ useMIRCuts (cutting-strategies.ts:74-212, branch-and-cut.ts:38-51)
+def test_mir_primitives_match_oracle():
+    """addLowerBoundMIRCut / addUpperBoundMIRCut / applyMIRCuts / computeFractionalVolume on a solved root, bit for bit."""
+    from jslpsolver_b200 import problems
+    it = problems.dense_packing_lp_tableau(19, 13, seed=4)
+    it.integerIndices = np.array([13 + j for j in range(0, 19, 2)], dtype=np.int32)
+    o = oracle_lp(it)
+    g = gpu_lp(it, 2)
+    o.simplex(); g.simplex()
+    assert same_bits(g.computeFractionalVolume(True), o.fractional_volume(True))
+    assert same_bits(g.computeFractionalVolume(False), o.fractional_volume(False))
+    for r in range(0, o.state().height):
+        assert g.addLowerBoundMIRCut(r) == o.add_mir_cut(r), r
+    assert g.height == o.state().height and same_bits(g.matrix2d(), o.matrix())
+    assert np.array_equal(g.varIndexByRow, o.maps()[0])
+    for r in (1, 2, 5):
+        assert g.addUpperBoundMIRCut(r) == o.add_mir_cut(r, upper=True), r
+    assert same_bits(g.matrix2d(), o.matrix())
+    o.simplex(); g.simplex()
+    assert_lp_parity(g, o, "after MIR cuts")
+    o.apply_mir_cuts(); g.applyMIRCuts()
+    assert g.height == o.state().height and same_bits(g.matrix2d(), o.matrix())
+
+
+@pytest.mark.parametrize("fx", [f for f in BUNDLE["fixtures"] if (f["model"].get("ints") or f["model"].get("binaries"))],
+                         ids=lambda f: f["file"])
+def test_mip_fixture_with_mir_cuts_matches_oracle(fx):
+    """options.useMIRCuts: same node sequence, same final tableau as the oracle's restatement of the MIR loop."""
+    import jslpsolver_b200 as J
+    from oracle import ref_model
+    jm = strip_timeouts(fx["model"])
+    jm["options"] = dict(jm.get("options") or {}, useMIRCuts=True)
+    osol = ref_model.solve_full(jm, fast_cycles=True, node_log=1 << 20)
+    if osol.tableau is None:
+        pytest.skip("decided by presolve")
+    s = J.Solver()
+    s.max_spec_batch = 8
+    gsol = s.Solve(jm, full=True)
+    gt = gsol._tableau
+    onl, gnl = osol.tableau.node_log(), gt.node_log()
+    assert gnl.shape == onl.shape, (gnl.shape, onl.shape)
+    for i in range(len(onl)):
+        a, b = gnl[i], onl[i]
+        ok = all(a[k] == b[k] for k in (0, 1, 2, 4, 5, 7)) and same_bits(a[6], b[6]) and (not b[2] or same_bits(a[3], b[3]))
+        assert ok, f"node {i}: gpu={a.tolist()} oracle={b.tolist()}"
+    assert gt.branchAndCutIterations == osol.state.bncIterations
+    assert same_bits(gt.matrix2d(), osol.tableau.matrix())
+    assert np.array_equal(gt.varIndexByRow, osol.tableau.maps()[0])
+    assert s._simplified(gsol) == ref_model.simplify(osol)
+    assert same_bits(gt.bestPossibleEval, osol.state.bestPossibleEval) and gt.lastBnbStatus.feasible == osol.state.feasible

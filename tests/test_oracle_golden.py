@@ -127,3 +127,66 @@ def test_solver_options_known_answers():
         "variables": {"a": {"profit": 10, "budget": 10}, "b": {"profit": 8, "budget": 10}},
         "ints": {"a": 1, "b": 1}, "tolerance": 0}))
     assert r["feasible"] is True and r["result"] == 100
+
+
+# ------------------------------------------------------------------ useMIRCuts (cutting-strategies.ts:74-212, branch-and-cut.ts:38-51)
+def _mir_tableau():
+    """The mock of cutting-strategies.test.ts:185-199: width 4, height 3, row 1 basic variable integer with right-hand
+    side 5.3, column variables y (integer) and z (continuous)."""
+    M = np.zeros((3, 4))
+    M[1] = [5.3, 2.5, -1.5, 0.25]
+    M[2] = [4.0, 1.0, 1.0, 1.0]
+    vrow = np.array([-1, 1, 0], dtype=np.int32)
+    vcol = np.array([-1, 2, 3, 4], dtype=np.int32)
+    return ref_model.OracleTableau(M, vrow, vcol, precision=1e-9, integers=[1, 2])
+
+
+def test_mir_cut_known_answers():
+    """The reference's own unit tests pin structure only (cutting-strategies.test.ts:145-330): false on the cost row, on a
+    non-integer or undefined basic variable, on an integral or near-integral right-hand side; true + one more row on a
+    fractional one.  The coefficient formulas are checked here against a direct evaluation of cutting-strategies.ts:116-131
+    and 174-193."""
+    import math
+    t = _mir_tableau()
+    assert not t.add_mir_cut(0) and not t.add_mir_cut(0, upper=True)          # cost row
+    assert not t.add_mir_cut(2) and not t.add_mir_cut(2, upper=True)          # basic variable 0 is not integer
+    t2 = _mir_tableau()
+    X = t2.matrix(); X[1, 0] = 5.0
+    t2 = ref_model.OracleTableau(X, *t2.maps(), precision=1e-9, integers=[1, 2])
+    assert not t2.add_mir_cut(1)                                              # integral right-hand side
+    X[1, 0] = 5.0000001
+    t3 = ref_model.OracleTableau(X, np.array([-1, 1, 0], dtype=np.int32), np.array([-1, 2, 3, 4], dtype=np.int32),
+                                 precision=1e-6, integers=[1, 2])
+    assert not t3.add_mir_cut(1)                                              # near-integral counts as integral
+    assert t.add_mir_cut(1)
+    Y = t.matrix()
+    assert Y.shape == (4, 4) and t.maps()[0][3] == 5                          # new slack takes the next element index
+    f = 5.3 - math.floor(5.3)
+    want = [math.floor(5.3) - 5.3,
+            (math.floor(2.5) + max(0, 2.5 - math.floor(2.5) - f) / (1 - f)) - 2.5,   # y is integer
+            min(0, -1.5 / (1 - f)) - (-1.5),                                           # z is continuous
+            min(0, 0.25 / (1 - f)) - 0.25]                                             # var 4: undefined -> continuous rule
+    assert Y[3].tolist() == want
+    assert t.add_mir_cut(1, upper=True)
+    Z = t.matrix()
+    tc = 2.5 - math.floor(2.5)
+    assert Z[4].tolist() == [-f, (-(1 - tc) * f) / tc, (-1.5 * f) / (1 - f), -0.25]
+    assert t.fractional_volume(False) == 0 or t.fractional_volume(True) >= 0
+
+
+def test_mir_cuts_are_valid_inequalities():
+    """Mixed-integer rounding cuts cut off no integer point: with options.useMIRCuts every MIP fixture keeps its optimum
+    (the reference's options test only asks for feasible && result > 0, solver.options.test.ts:252-272)."""
+    model = {"optimize": "profit", "opType": "max", "constraints": {"resource": {"max": 100}},
+             "variables": {"x": {"profit": 10, "resource": 7}, "y": {"profit": 15, "resource": 11}},
+             "ints": {"x": 1, "y": 1}, "options": {"useMIRCuts": True}}
+    res = ref_model.Solve(model)
+    assert res["feasible"] and res["result"] > 0 and res["result"] == ref_model.Solve(dict(model, options={}))["result"]
+    for fx in BUNDLE["fixtures"]:
+        m = strip_timeouts(fx["model"])
+        if not (m.get("ints") or m.get("binaries")) or m.get("tolerance") or (m.get("options") or {}).get("tolerance"):
+            continue  # a tolerance accepts any incumbent within it: the path, hence the answer, may differ
+        m["options"] = dict(m.get("options") or {}, useMIRCuts=True)
+        r = ref_model.Solve(m, fast_cycles=True)
+        bad = [b for b in compare_solutions(r, fx["expects"]) if b.startswith(("result", "feasible"))]
+        assert not bad, (fx["file"], bad)
