@@ -176,7 +176,8 @@ def run_mip_leg(args, torch, dist, rank, world):
                     f"BASELINE.json configs[4]; Model.solve() capped at {args.mip_nodes} committed nodes (no incumbent "
                     f"exists within thousands of nodes: a tolerance cannot end it); best of {args.mip_reps}",
         "n_gpus": world, "spec_width": K, "scaling": "strong",
-        "total_ms": r["total_ms"], "root_lp_ms": r["root_ms"], "node_phase_ms": r["node_phase_ms"],
+        "total_ms": r["total_ms"], "branch_and_cut_ms": r["gpu_ms"], "root_lp_ms": r["root_ms"],
+        "node_phase_ms": r["node_phase_ms"], "host_front_end_ms": r["total_ms"] - r["gpu_ms"],
         "committed_nodes": r["committed_nodes"], "node_lps": r["node_lps_all_ranks"], "rounds": r["rounds"],
         "node_lps_per_s": non_root / (r["node_phase_ms"] * 1e-3),
         "committed_per_s": (r["committed_nodes"] - 1) / (r["node_phase_ms"] * 1e-3),
@@ -187,6 +188,10 @@ def run_mip_leg(args, torch, dist, rank, world):
         "roofline": {"bound": "hbm", "kernel": "k_pivot_step<256,2,flat8> over node slots (grid (G+2) x B)",
                      "achieved": slot_gbs, "peak": peak * world, "unit": "GB/s",
                      "frac": (slot_gbs / (peak * world)) if slot_gbs else None,
+                     "timing": "total_ms = wall clock of Model.solve() between barriers, slowest rank (presolve + tableau "
+                               "build in the Python host mirror = host_front_end_ms, upload, branch and cut, read-back); "
+                               "branch_and_cut_ms = CUDA events around jslp_branch_and_cut (root LP + node phase + final "
+                               "re-solve)",
                      "note": "algorithmic bytes of the pivots executed in node slots (16 x rows x stride each, all "
                              "ranks) / wall time of the slot-batch graphs incl. restore, cut rows, idle slot steps "
                              "and host polls (slowest rank); the B tableau pairs exceed L2, so this one is HBM-bound"},
@@ -204,10 +209,11 @@ def run_mip_leg(args, torch, dist, rank, world):
     return out
 
 
-def cpu_sample(it, pivots: int):
-    """The reference's CPU path restated (oracle/, single thread) on the first `pivots` pivots."""
+def cpu_sample(it, pivots: int, check_cycles: bool = True):
+    """The reference's CPU path restated (oracle/, single thread) on the first `pivots` pivots; with check_cycles
+    the literal O(k^2)-per-pivot checkForCycles scan (simplex.ts:415-440, the reference's default) is included."""
     from oracle import ref_model
-    t = ref_model.OracleTableau(it.matrix, it.varIndexByRow, it.varIndexByCol, check_cycles=True, fast_cycles=False)
+    t = ref_model.OracleTableau(it.matrix, it.varIndexByRow, it.varIndexByCol, check_cycles=check_cycles, fast_cycles=False)
     t.set_pivot_limit(pivots)
     t0 = time.perf_counter()
     st = t.simplex()
@@ -401,10 +407,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             line["mip"] = mip
         if world == 1 and not args.no_cpu:
             p, dt = cpu_sample(it, args.cpu_pivots)
+            p2, dt2 = cpu_sample(it, args.cpu_pivots, check_cycles=False)
             line["cpu_baseline"] = {
                 "value": p / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"first {p} pivots of the same solve ({dt:.1f} s); oracle/ C restatement, 1 thread "
-                          f"(the reference is single-threaded; box has {os.cpu_count()} host cores)"}
+                "value_without_cycle_check": p2 / dt2,
+                "sample": f"first {p} pivots of the same solve ({dt:.1f} s with the reference's default literal "
+                          f"checkForCycles scan -- cheap this early in a solve, it grows as k^2 --, {dt2:.1f} s with "
+                          f"options.exitOnCycles false); oracle/ C restatement, 1 thread (the reference is "
+                          f"single-threaded; box has {os.cpu_count()} host cores; no Node.js on the box)"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         from jslpsolver_b200 import distributed as D

@@ -569,10 +569,29 @@ static int step_grid(const jslp_tab *t) {
 
 // The ping-pong step applies to a whole solve or not at all (the graph holds one kernel): no optional
 // objectives, the second tableau buffer, and at most 32 rows per row CTA (one warp runs the look-ahead).
+// The selector CTAs of the ping-pong step wait for messages from every row CTA of the same launch, so the whole
+// grid has to be co-resident: checked against the occupancy the runtime reports for this instantiation and its
+// dynamic shared memory (a wide tableau stages a long pivot row and may fit one CTA per SM only).  When it is not,
+// the in-place step -- which has no intra-launch dependency -- runs instead.
+static bool pp_coresident(const jslp_tab *t, int grid) {
+    const StepVariant &sv = step_variant(t);
+    const int smem = t->stride * 8;
+    static thread_local int c_key = -1, c_val = 0;
+    const int key = variant_index(t) * 1000003 + smem;
+    if (key != c_key) {
+        int nb = 0;
+        cudaFuncSetAttribute(sv.fn_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sv.fn_pp, sv.threads, (size_t)smem) != cudaSuccess) nb = 0;
+        c_key = key; c_val = nb;
+    }
+    return (int64_t)c_val * t->ctx->num_sms >= grid;
+}
+
 static bool use_pp(const jslp_tab *t) {
     const int grid = step_grid(t);
     if (!(t->pingpong && t->lookahead && t->nOpt == 0 && grid >= 3 && t->hd.M2 != nullptr)) return false;
-    return t->H / (grid - 2) + 1 <= 32;
+    if (t->H / (grid - 2) + 1 > 32) return false;
+    return pp_coresident(t, grid);
 }
 
 // (re)allocates the buffers that depend on the step grid: look-ahead partials, debug timeline

@@ -77,7 +77,14 @@ static int slots_for(const jslp_tab *t, int rowcap, int want) {
     if (t->node_slots == 0 || want < 2) return 0;
     if (!(t->pingpong && t->lookahead && t->nOpt == 0) || t->engine == 1) return 0;
     const StepVariant &sv = STEP_VARIANTS[t->slot_variant];
-    const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
+    int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
+    {   // every CTA of the slot batch must be co-resident (selectors wait for row CTAs of the same launch)
+        int nb = 0;
+        cudaFuncSetAttribute(sv.fn_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, t->stride * 8);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sv.fn_pp, sv.threads, (size_t)t->stride * 8) != cudaSuccess) nb = 0;
+        per_sm = std::min(per_sm, nb);
+        if (per_sm < 1) return 0;
+    }
     const int C = t->ctx->num_sms * per_sm;
     int geom = 0;
     for (int b = 1; b <= 64; b++) {
@@ -100,7 +107,11 @@ static int ensure_slots(jslp_tab *t, int B, int need_rowcap) {
     jslp_ctx *ctx = t->ctx;
     cudaStream_t s = ctx->stream;
     const StepVariant &sv = STEP_VARIANTS[t->slot_variant];
-    const int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
+    int per_sm = t->grid_per_sm > 0 ? t->grid_per_sm : sv.ctas_per_sm;
+    {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sv.fn_pp, sv.threads, (size_t)t->stride * 8) == cudaSuccess) per_sm = std::min(per_sm, std::max(1, nb));
+    }
     const int G = ctx->num_sms * per_sm / B - 2;
     const int S = t->slot_steps;
     const int stride = t->stride;
@@ -403,6 +414,7 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
         CK(cudaMemcpyAsync(rb.h_logs, rb.d_logs, sizeof(int4) * (size_t)n * log_cap, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }
+    std::vector<int> redo_list;
     for (int i = 0; i < n; i++) {
         const NodeResult &r = rb.h_out[i].r;
         jslp_bnb::NodeEval &ev = nodes[i]->ev;
@@ -417,11 +429,7 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
                 if (cycle_hit(h, &cs, &cl)) redo = true;
             }
         }
-        if (redo) {
-            rc = eval_node_streaming(t, *nodes[i], check_cycles, ev);
-            if (rc) return rc;
-            continue;
-        }
+        if (redo) { redo_list.push_back(i); continue; }  // second pass: the HBM path may reuse rb's buffers
         ev.valid = true;
         ev.pivots = r.p1 + r.p2;
         ev.optimal = r.status == ST_OPTIMAL;
@@ -435,6 +443,10 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
             ev.evaluation = 0.0;  // infeasible: never read by the commit loop; rank-independent on the wire
         }
         ev.is_integral = r.is_integral; ev.branch_var = r.branch_var; ev.branch_value = r.branch_value;
+    }
+    for (int i : redo_list) {
+        rc = eval_node_streaming(t, *nodes[i], check_cycles, nodes[i]->ev);
+        if (rc) return rc;
     }
     return JSLP_OK;
 }

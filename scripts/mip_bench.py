@@ -54,6 +54,8 @@ def main():
     if os.environ.get("NO_KNAP", "0") == "1":
         workloads = workloads[:-1]
     widths = [int(x) for x in os.environ.get("SPEC", "1,8,32,128").split(",")]
+    if os.environ.get("SPEC_PER_RANK"):  # speculation width proportional to the number of ranks
+        widths = [int(x) * world for x in os.environ["SPEC_PER_RANK"].split(",")]
     spin = torch.zeros(1 << 26, device="cuda")
     for name, model, max_nodes in workloads:
         # the knapsack root LP alone is ~85k pivots of 25 MB: minutes on one CPU core (measured in the
