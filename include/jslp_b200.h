@@ -155,6 +155,30 @@ int jslp_apply_cuts(jslp_tab *tab, const jslp_cut *cuts, int n, int check_cycles
 int jslp_is_integral(jslp_tab *tab, int *is_integral);
 int jslp_most_fractional(jslp_tab *tab, int32_t *var_index, double *value);
 
+/* The dynamic-modification API on the device-resident tableau (dynamic-modification.ts:16-55,78-316): edits after a
+ * solve without rebuilding / re-uploading it.  Constraints and variables are named by their element index
+ * (Constraint.index == its slack's index, Variable.index); availableIndexes and the Constraint / Variable objects stay
+ * host bookkeeping.  opt_slot: -1 = priority 0 (cost row), k = the k-th uploaded optional objective.
+ *   put_in_base / take_out_of_base   == Tableau.putInBase / takeOutOfBase (may pivot); *row / *col = where it ended
+ *   update_rhs                       == updateRightHandSide(constraint, difference)
+ *   update_coefficient               == updateConstraintCoefficient(constraint, variable, difference)
+ *   update_cost                      == updateCost(variable, difference)
+ *   add_constraint / remove_constraint == addConstraint(constraint) / removeConstraint(constraint); terms in order
+ *   add_variable / remove_variable   == addVariable(variable) / removeVariable(variable); cost_entry is the signed
+ *                                       cost-row entry (isMinimization ? -cost : cost)                            */
+int jslp_put_in_base(jslp_tab *tab, int var_index, int *row);
+int jslp_take_out_of_base(jslp_tab *tab, int var_index, int *col);
+int jslp_update_rhs(jslp_tab *tab, int constraint_index, double difference);
+int jslp_update_coefficient(jslp_tab *tab, int constraint_index, int var_index, double difference);
+int jslp_update_cost(jslp_tab *tab, int var_index, int opt_slot, double difference);
+int jslp_add_constraint(jslp_tab *tab, int is_upper_bound, double rhs, int slack_index, const int32_t *term_var,
+                        const double *term_coef, int n_terms);
+int jslp_remove_constraint(jslp_tab *tab, int slack_index);
+int jslp_add_variable(jslp_tab *tab, int var_index, double cost_entry, int opt_slot, int is_integer, int is_unrestricted);
+/* Tableau's scalar bookkeeping for the host mirror: {width, height, nVars, lastElementIndex, row stride, row capacity} */
+int jslp_tab_info(jslp_tab *tab, int32_t *out6);
+int jslp_remove_variable(jslp_tab *tab, int var_index);
+
 /* Read-back for updateVariableValues / generateSolutionSet / getSolution
  * (dynamic-modification.ts:57-76, solution.ts:35-60).  Any pointer may be NULL.
  *   matrix     height*width doubles (stride == width)   rhs_col   height doubles

@@ -80,6 +80,16 @@ SYMBOLS = [
     ("jslp_add_mir_cut", C.c_int, [P, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     ("jslp_apply_mir_cuts", C.c_int, [P, C.POINTER(C.c_int)]),
     ("jslp_fractional_volume", C.c_int, [P, C.c_int, C.POINTER(C.c_double)]),
+    ("jslp_put_in_base", C.c_int, [P, C.c_int, C.POINTER(C.c_int)]),
+    ("jslp_take_out_of_base", C.c_int, [P, C.c_int, C.POINTER(C.c_int)]),
+    ("jslp_update_rhs", C.c_int, [P, C.c_int, C.c_double]),
+    ("jslp_update_coefficient", C.c_int, [P, C.c_int, C.c_int, C.c_double]),
+    ("jslp_update_cost", C.c_int, [P, C.c_int, C.c_int, C.c_double]),
+    ("jslp_add_constraint", C.c_int, [P, C.c_int, C.c_double, C.c_int, P, P, C.c_int]),
+    ("jslp_remove_constraint", C.c_int, [P, C.c_int]),
+    ("jslp_add_variable", C.c_int, [P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]),
+    ("jslp_tab_info", C.c_int, [P, P]),
+    ("jslp_remove_variable", C.c_int, [P, C.c_int]),
     ("jslp_is_integral", C.c_int, [P, C.POINTER(C.c_int)]),
     ("jslp_most_fractional", C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     ("jslp_download", C.c_int, [P, P, P, P, P, P, P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

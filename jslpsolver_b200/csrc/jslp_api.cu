@@ -230,6 +230,15 @@ static int push_desc(jslp_tab *t) {
     return JSLP_OK;
 }
 
+// phase-2 partial pricing parameters (simplex.ts:118-127), a function of the current width
+static void set_pricing_params(jslp_tab *t) {
+    const int nColumns = t->W - 1;
+    int bs = (int)std::floor(std::sqrt((double)nColumns));
+    bs = std::min(500, std::max(50, bs));
+    t->hd.batch_size = bs;
+    t->hd.use_partial = nColumns > bs * 2;
+}
+
 static int alloc_rows(jslp_tab *t, int rowcap) {
     // (re)allocates every buffer whose size depends on the row capacity, preserving contents
     double *M = nullptr, *M2 = nullptr, *pcol = nullptr;
@@ -273,10 +282,10 @@ extern "C" int jslp_tab_create(jslp_ctx *ctx, int width, int height, int row_cap
     t->lastElementIndex = t->n_index;
     int rc = alloc_rows(t, row_capacity);
     if (rc) { delete t; return rc; }
-    CK(cudaMalloc(&t->hd.vcol, sizeof(int) * (size_t)width));
+    CK(cudaMalloc(&t->hd.vcol, sizeof(int) * (size_t)t->stride));  // stride entries: addVariable grows W in place
     CK(cudaMalloc(&t->hd.prow, sizeof(double) * (size_t)t->stride));
     CK(cudaMalloc(&t->hd.crow, sizeof(double) * (size_t)t->stride));
-    CK(cudaMalloc(&t->hd.optflag, (size_t)width));
+    CK(cudaMalloc(&t->hd.optflag, (size_t)t->stride));
     t->hd.plog_cap = 4096;
     CK(cudaMalloc(&t->hd.plog, sizeof(int4) * (size_t)t->hd.plog_cap));
     CK(cudaMalloc(&t->d_T, sizeof(TabDev)));
@@ -291,12 +300,7 @@ extern "C" int jslp_tab_create(jslp_ctx *ctx, int width, int height, int row_cap
     CK(cudaMallocHost(&t->h_count, sizeof(int)));
     CK(cudaMemsetAsync(t->d_rec, 0, sizeof(Rec), ctx->stream));
     CK(cudaMemsetAsync(t->hd.prow, 0, sizeof(double) * (size_t)t->stride, ctx->stream));
-    // phase-2 partial pricing parameters (simplex.ts:118-127)
-    const int nColumns = width - 1;
-    int bs = (int)std::floor(std::sqrt((double)nColumns));
-    bs = std::min(500, std::max(50, bs));
-    t->hd.batch_size = bs;
-    t->hd.use_partial = nColumns > bs * 2;
+    set_pricing_params(t);
     rc = push_desc(t);
     if (rc) { delete t; return rc; }
     *out = t;
@@ -713,7 +717,7 @@ static int ensure_snapshot(jslp_tab *t, int slot) {
     CK(cudaMalloc(&sn.M, sizeof(double) * (size_t)t->rowcap * t->stride));
     CK(cudaMalloc(&sn.pcol, sizeof(double) * (size_t)t->rowcap));
     CK(cudaMalloc(&sn.vrow, sizeof(int) * (size_t)t->rowcap));
-    CK(cudaMalloc(&sn.vcol, sizeof(int) * (size_t)t->W));
+    CK(cudaMalloc(&sn.vcol, sizeof(int) * (size_t)t->stride));
     CK(cudaMalloc(&sn.prow, sizeof(double) * (size_t)t->stride));
     CK(cudaMalloc(&sn.rec, sizeof(Rec)));
     if (t->nOpt > 0) {
@@ -1073,7 +1077,7 @@ extern "C" int jslp_save(jslp_tab *t) {
         free_saved(sv);
         CK(cudaMalloc(&sv.M, sizeof(double) * (size_t)t->rowcap * t->stride));
         CK(cudaMalloc(&sv.vrow, sizeof(int) * (size_t)t->rowcap));
-        CK(cudaMalloc(&sv.vcol, sizeof(int) * (size_t)t->W));
+        CK(cudaMalloc(&sv.vcol, sizeof(int) * (size_t)t->stride));
         if (t->nOpt > 0) CK(cudaMalloc(&sv.opt, sizeof(double) * (size_t)t->nOpt * t->stride));
         sv.rowcap = t->rowcap;
     }
@@ -1329,5 +1333,6 @@ extern "C" int jslp_pivot_log(jslp_tab *t, int32_t *entries, int cap, int *n) {
     return JSLP_OK;
 }
 
+#include "jslp_dynamic.cuh"
 #include "jslp_comm.cuh"
 #include "jslp_bnb.cuh"

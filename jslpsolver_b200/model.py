@@ -85,27 +85,36 @@ class Constraint:  # expressions.ts:96-203
     def terms(self) -> list[Term]:
         return list(self.coef.values())
 
-    def addTerm(self, coefficient: float, variable: Variable) -> "Constraint":
+    def addTerm(self, coefficient: float, variable: Variable) -> "Constraint":  # expressions.ts:119-137
         t = self.coef.get(variable.index)
         if t is None:
             self.coef[variable.index] = Term(variable, coefficient)
+            self.model.updateConstraintCoefficient(self, variable, -coefficient if self.isUpperBound else coefficient)
         else:
-            t.coefficient = t.coefficient + coefficient
-        self.model._dirty()
+            self.setVariableCoefficient(t.coefficient + coefficient, variable)
         return self
 
-    def setVariableCoefficient(self, newCoefficient: float, variable: Variable) -> "Constraint":
+    def setVariableCoefficient(self, newCoefficient: float, variable: Variable) -> "Constraint":  # expressions.ts:158-184
+        if variable.index == -1:
+            return self
         t = self.coef.get(variable.index)
         if t is None:
-            self.coef[variable.index] = Term(variable, newCoefficient)
-        else:
+            self.addTerm(newCoefficient, variable)
+        elif newCoefficient != t.coefficient:
+            difference = newCoefficient - t.coefficient
+            if self.isUpperBound:
+                difference = -difference
             t.coefficient = newCoefficient
-        self.model._dirty()
+            self.model.updateConstraintCoefficient(self, variable, difference)
         return self
 
-    def setRightHandSide(self, newRhs: float) -> "Constraint":
-        self.rhs = newRhs
-        self.model._dirty()
+    def setRightHandSide(self, newRhs: float) -> "Constraint":  # expressions.ts:144-156
+        if newRhs != self.rhs:
+            difference = newRhs - self.rhs
+            if self.isUpperBound:
+                difference = -difference
+            self.rhs = newRhs
+            self.model.updateRightHandSide(self, difference)
         return self
 
     def relax(self, weight=None, priority=None) -> None:
@@ -200,15 +209,57 @@ class Model:
     def nVariables(self) -> int:
         return len(self.variables)
 
-    def _dirty(self) -> None:
+    def _new_index(self) -> int:  # tableau.getNewElementIndex (tableau.ts:393-401): the device tableau's once it exists
         if self.tableauInitialized:
-            raise NotImplementedError(
-                "editing a model after solve() (dynamic-modification.ts) is outside the hot-path scope")
-
-    def _new_index(self) -> int:  # tableau.getNewElementIndex before initialize (tableau.ts:393-401)
+            return self.tableau.getNewElementIndex()
         i = self._next_index
         self._next_index += 1
         return i
+
+    # ---- dynamic model modification (model.ts:196-273): edits after solve() go to the device tableau
+    def updateRightHandSide(self, constraint, difference: float) -> "Model":
+        if self.tableauInitialized:
+            self.tableau.updateRightHandSide(constraint, difference)
+        return self
+
+    def updateConstraintCoefficient(self, constraint, variable, difference: float) -> "Model":
+        if self.tableauInitialized:
+            self.tableau.updateConstraintCoefficient(constraint, variable, difference)
+        return self
+
+    def setCost(self, cost: float, variable) -> "Model":
+        difference = cost - variable.cost
+        if not self.isMinimization:
+            difference = -difference
+        variable.cost = cost
+        if self.tableauInitialized:
+            self.tableau.updateCost(variable, difference)
+        return self
+
+    def _removeConstraint(self, constraint) -> None:
+        if constraint not in self.constraints:
+            return
+        self.constraints.remove(constraint)
+        if self.tableauInitialized:
+            self.tableau.removeConstraint(constraint)
+        if constraint.relaxation is not None:
+            self.removeVariable(constraint.relaxation)
+
+    def removeConstraint(self, constraint) -> "Model":
+        if getattr(constraint, "isEquality", False):
+            self._removeConstraint(constraint.upperBound)
+            self._removeConstraint(constraint.lowerBound)
+        else:
+            self._removeConstraint(constraint)
+        return self
+
+    def removeVariable(self, variable) -> "Model":
+        if variable not in self.variables:
+            return self
+        self.variables.remove(variable)
+        if self.tableauInitialized:
+            self.tableau.removeVariable(variable)
+        return self
 
     def minimize(self) -> "Model":
         self.isMinimization = True
@@ -218,11 +269,12 @@ class Model:
         self.isMinimization = False
         return self
 
-    def _constraint(self, rhs: float, upper: bool) -> Constraint:
-        self._dirty()
+    def _constraint(self, rhs: float, upper: bool) -> Constraint:  # model.ts:103-124
         c = Constraint(rhs, upper, self._new_index(), self)
         self.variablesPerIndex[c.index] = c.slack
         self.constraints.append(c)
+        if self.tableauInitialized:
+            self.tableau.addConstraint(c)
         return c
 
     def smallerThan(self, rhs: float) -> Constraint:
@@ -235,7 +287,6 @@ class Model:
         return Equality(self._constraint(rhs, True), self._constraint(rhs, False))
 
     def addVariable(self, cost=None, id=None, isInteger=False, isUnrestricted=False, priority=None) -> Variable:
-        self._dirty()
         if isinstance(priority, str):
             priority = PRIORITY_NAMES.get(priority, 0)
         idx = self._new_index()
@@ -247,6 +298,8 @@ class Model:
         self.variablesPerIndex[idx] = v
         if isUnrestricted:
             self.unrestrictedVariables[idx] = True
+        if self.tableauInitialized:  # model.ts:191-193
+            self.tableau.addVariable(v)
         return v
 
     def _relaxation_variable(self, weight, priority) -> Optional[Variable]:  # expressions.ts:73-94

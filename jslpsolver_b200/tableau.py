@@ -124,6 +124,7 @@ class GpuTableau:
         self.node_slots = None    # JSLP_OPT_NODE_SLOTS (None = library default: auto)
         self.slot_steps = None    # JSLP_OPT_SLOT_STEPS
         self.options: dict = {}   # JSLP_OPT_* -> value, applied after every upload (tuning aids)
+        self.availableIndexes: list = []   # tableau.ts:77
         self._cache: dict = {}
         self._cache_log = None
 
@@ -249,10 +250,93 @@ class GpuTableau:
         self._refresh_dims()
 
     def _refresh_dims(self) -> None:
-        w, h = C.c_int32(), C.c_int32()
-        _lib.check(self.context.lib.jslp_download(self._h(), None, None, None, None, None, None, C.byref(w), C.byref(h)))
-        self.width, self.height = w.value, h.value
+        info = (C.c_int32 * 6)()
+        _lib.check(self.context.lib.jslp_tab_info(self._h(), info))
+        self.width, self.height, self.nVars, self.lastElementIndex = info[0], info[1], info[2], info[3]
         self._cache.clear()
+
+    def getNewElementIndex(self) -> int:  # tableau.ts:393-401
+        if self.availableIndexes:
+            return self.availableIndexes.pop()
+        self._refresh_dims()
+        index = self.lastElementIndex
+        self.lastElementIndex += 1
+        return index
+
+    # ------------------------------------------------------------------ dynamic modification (dynamic-modification.ts)
+    def _opt_slot(self, priority) -> int:
+        if not priority:
+            return -1
+        if priority not in self.optionalPriorities:
+            raise JslpError("an optional objective with a new priority needs setModel() again (the uploaded set is fixed)")
+        return self.optionalPriorities.index(priority)
+
+    def putInBase(self, varIndex: int) -> int:
+        r = C.c_int()
+        _lib.check(self.context.lib.jslp_put_in_base(self._h(), int(varIndex), C.byref(r)))
+        self._cache.clear()
+        return r.value
+
+    def takeOutOfBase(self, varIndex: int) -> int:
+        c = C.c_int()
+        _lib.check(self.context.lib.jslp_take_out_of_base(self._h(), int(varIndex), C.byref(c)))
+        self._cache.clear()
+        return c.value
+
+    def updateRightHandSide(self, constraint, difference: float) -> None:
+        idx = constraint if isinstance(constraint, int) else constraint.index
+        _lib.check(self.context.lib.jslp_update_rhs(self._h(), int(idx), float(difference)))
+        self._cache.clear()
+
+    def updateConstraintCoefficient(self, constraint, variable, difference: float) -> None:
+        ci = constraint if isinstance(constraint, int) else constraint.index
+        vi = variable if isinstance(variable, int) else variable.index
+        if ci == vi:  # dynamic-modification.ts:114-118
+            raise ValueError("[Tableau.updateConstraintCoefficient] constraint index should not be equal to variable index !")
+        _lib.check(self.context.lib.jslp_update_coefficient(self._h(), int(ci), int(vi), float(difference)))
+        self._cache.clear()
+
+    def updateCost(self, variable, difference: float, priority: int = 0) -> None:
+        vi = variable if isinstance(variable, int) else variable.index
+        pr = priority if isinstance(variable, int) else variable.priority
+        _lib.check(self.context.lib.jslp_update_cost(self._h(), int(vi), self._opt_slot(pr), float(difference)))
+        self._cache.clear()
+
+    def addConstraint(self, constraint=None, *, isUpperBound=None, rhs=None, index=None, terms=None) -> None:
+        if constraint is not None:
+            isUpperBound, rhs, index = constraint.isUpperBound, constraint.rhs, constraint.index
+            terms = [(t.variable.index, t.coefficient) for t in constraint.terms]
+        terms = terms or []
+        tv = np.ascontiguousarray([v for v, _ in terms], dtype=np.int32)
+        tc = np.ascontiguousarray([c for _, c in terms], dtype=np.float64)
+        _lib.check(self.context.lib.jslp_add_constraint(self._h(), int(bool(isUpperBound)), float(rhs), int(index),
+                                                        tv.ctypes.data if len(terms) else None,
+                                                        tc.ctypes.data if len(terms) else None, len(terms)))
+        self._refresh_dims()
+
+    def removeConstraint(self, constraint) -> None:
+        idx = constraint if isinstance(constraint, int) else constraint.index
+        _lib.check(self.context.lib.jslp_remove_constraint(self._h(), int(idx)))
+        self.availableIndexes.append(idx)          # dynamic-modification.ts:246
+        if not isinstance(constraint, int):
+            constraint.slack.index = -1            # :248
+        self._refresh_dims()
+
+    def addVariable(self, variable=None, *, index=None, cost=0.0, priority=0, isInteger=False, isUnrestricted=False) -> None:
+        if variable is not None:
+            index, cost, priority, isInteger = variable.index, variable.cost, variable.priority, variable.isInteger
+            isUnrestricted = bool(self.model is not None and self.model.unrestrictedVariables.get(index))
+        is_min = True if self.model is None else self.model.isMinimization
+        entry = -cost if is_min else cost                      # dynamic-modification.ts:258
+        _lib.check(self.context.lib.jslp_add_variable(self._h(), int(index), float(entry), self._opt_slot(priority),
+                                                      int(bool(isInteger)), int(bool(isUnrestricted))))
+        self._refresh_dims()
+
+    def removeVariable(self, variable) -> None:
+        idx = variable if isinstance(variable, int) else variable.index
+        _lib.check(self.context.lib.jslp_remove_variable(self._h(), int(idx)))
+        self.availableIndexes.append(idx)          # dynamic-modification.ts:313
+        self._refresh_dims()
 
     # ------------------------------------------------------------------ cuts / MIP helpers
     @staticmethod

@@ -17,6 +17,8 @@
  *   cutting-strategies.ts:16-72 addCutConstraints -> orc_add_cuts
  *   cutting-strategies.ts:74-212 addLowerBoundMIRCut / addUpperBoundMIRCut / applyMIRCuts -> orc_add_mir_cut / orc_apply_mir_cuts
  *   mip-utils.ts:67-98  computeFractionalVolume -> orc_fractional_volume
+ *   dynamic-modification.ts:16-316 putInBase / takeOutOfBase / updateRightHandSide / updateConstraintCoefficient /
+ *                       updateCost / addConstraint / removeConstraint / addVariable / removeVariable -> orc_dm_*
  *   mip-utils.ts:43-61,100-126  isIntegral / getMostFractionalVar
  *   min-heap.ts:18-119  BranchMinHeap      -> heap_push / heap_pop
  *   branch-and-cut.ts:33-199    applyCuts / branchAndCut -> apply_cuts / orc_branch_and_cut
@@ -724,6 +726,175 @@ int orc_most_fractional(const orc_tab *t, double *val) {
     return sel;
 }
 
+/* ---- dynamic-modification.ts ---- */
+/* :16-34; returns the row, or -2 when no pivot element exists (the reference would call pivot(-1, c)) */
+int orc_dm_put_in_base(orc_tab *t, int varIndex) {
+    ensure_maps(t, varIndex + 1);
+    int r = t->rowOf[varIndex];
+    if (r == -1) {
+        const int c = t->colOf[varIndex];
+        for (int r1 = 1; r1 < t->H; r1++) {
+            const double coefficient = t->M[(size_t)r1 * t->W + c];
+            if (coefficient < -t->precision || t->precision < coefficient) { r = r1; break; }
+        }
+        if (r == -1) return -2;
+        orc_pivot(t, r, c);
+    }
+    return r;
+}
+
+/* :36-55 -- the scan bound is `this.height` in the reference (not the width); kept, reading the flat matrix */
+int orc_dm_take_out_of_base(orc_tab *t, int varIndex) {
+    ensure_maps(t, varIndex + 1);
+    int c = t->colOf[varIndex];
+    if (c == -1) {
+        const int r = t->rowOf[varIndex];
+        const size_t pivotRowOffset = (size_t)r * t->W, total = (size_t)t->H * t->W;
+        for (int c1 = 1; c1 < t->H; c1++) {
+            if (pivotRowOffset + c1 >= total) break;  /* undefined in JS: both comparisons false */
+            const double coefficient = t->M[pivotRowOffset + c1];
+            if (coefficient < -t->precision || t->precision < coefficient) { c = c1; break; }
+        }
+        if (c == -1 || c >= t->W) return -2;
+        orc_pivot(t, r, c);
+    }
+    return c;
+}
+
+/* :78-106 */
+void orc_dm_update_rhs(orc_tab *t, int constraintIndex, double difference) {
+    const int W = t->W, lastRow = t->H - 1;
+    const int constraintRow = t->rowOf[constraintIndex];
+    if (constraintRow == -1) {
+        const int slackColumn = t->colOf[constraintIndex];
+        for (int r = 0; r <= lastRow; r++) {
+            double *row = t->M + (size_t)r * W;
+            const double prod = difference * row[slackColumn];
+            row[0] -= prod;
+        }
+        for (int o = 0; o < t->nOpt; o++) {
+            double *rc = t->optRC + (size_t)o * W;
+            const double prod = difference * rc[slackColumn];
+            rc[0] -= prod;
+        }
+    } else {
+        t->M[(size_t)constraintRow * W] -= difference;
+    }
+}
+
+/* :108-135; returns 0, -1 for the reference's thrown Error, -2 when putInBase finds no pivot */
+int orc_dm_update_coefficient(orc_tab *t, int constraintIndex, int varIndex, double difference) {
+    if (constraintIndex == varIndex) return -1;
+    const int r = orc_dm_put_in_base(t, constraintIndex);
+    if (r < 0) return -2;
+    const int W = t->W;
+    double *row = t->M + (size_t)r * W;
+    const int colVar = t->colOf[varIndex];
+    if (colVar == -1) {
+        const double *vr = t->M + (size_t)t->rowOf[varIndex] * W;
+        for (int c = 0; c < W; c++) { const double prod = difference * vr[c]; row[c] += prod; }
+    } else {
+        row[colVar] -= difference;
+    }
+    return 0;
+}
+
+/* :137-160; optSlot = -1 for priority 0 (cost row), else the optional objective's position */
+void orc_dm_update_cost(orc_tab *t, int varIndex, int optSlot, double difference) {
+    const int W = t->W;
+    const int varColumn = t->colOf[varIndex];
+    if (varColumn == -1) {
+        const double *vr = t->M + (size_t)t->rowOf[varIndex] * W;
+        double *dst = optSlot < 0 ? t->M : t->optRC + (size_t)optSlot * W;
+        for (int c = 0; c < W; c++) { const double prod = difference * vr[c]; dst[c] += prod; }
+    } else {
+        t->M[varColumn] -= difference;
+    }
+}
+
+/* :162-220 */
+void orc_dm_add_constraint(orc_tab *t, int isUpperBound, double rhs, int slackIndex, const int *termVar,
+                           const double *termCoef, int nTerms) {
+    const double sign = isUpperBound ? 1 : -1;
+    const int lastRow = t->H, W = t->W;
+    ensure_rows(t, lastRow + 1);
+    double *row = t->M + (size_t)lastRow * W;
+    for (int c = 0; c < W; c++) row[c] = 0;
+    row[0] = sign * rhs;
+    for (int k = 0; k < nTerms; k++) {
+        const double coefficient = termCoef[k];
+        const int varIndex = termVar[k];
+        const int varRowIndex = t->rowOf[varIndex];
+        if (varRowIndex == -1) {
+            row[t->colOf[varIndex]] += sign * coefficient;
+        } else {
+            const double *vr = t->M + (size_t)varRowIndex * W;
+            const double sc = sign * coefficient;
+            for (int c = 0; c < W; c++) { const double prod = sc * vr[c]; row[c] -= prod; }
+        }
+    }
+    ensure_maps(t, slackIndex + 1);
+    t->vrow[lastRow] = slackIndex;
+    t->rowOf[slackIndex] = lastRow;
+    t->colOf[slackIndex] = -1;
+    t->H += 1;
+}
+
+/* :222-251 (availableIndexes is host bookkeeping of the caller) */
+int orc_dm_remove_constraint(orc_tab *t, int slackIndex) {
+    const int lastRow = t->H - 1, W = t->W;
+    const int r = orc_dm_put_in_base(t, slackIndex);
+    if (r < 0) return -2;
+    double *a = t->M + (size_t)r * W, *b = t->M + (size_t)lastRow * W;
+    for (int c = 0; c < W; c++) { const double tmp = b[c]; b[c] = a[c]; a[c] = tmp; }
+    t->vrow[r] = t->vrow[lastRow];
+    t->vrow[lastRow] = -1;
+    t->rowOf[slackIndex] = -1;
+    /* the reference leaves rowByVarIndex of the moved row's variable stale here (dynamic-modification.ts:241-243);
+       so does this restatement -- callers that go on must not rely on it, exactly as in the reference */
+    t->H -= 1;
+    return 0;
+}
+
+/* :253-302; costEntry = (isMinimization ? -cost : cost); optSlot = -1 for priority 0 */
+void orc_dm_add_variable(orc_tab *t, int varIndex, double costEntry, int optSlot) {
+    const int oldW = t->W, newW = oldW + 1, H = t->H;
+    double *nm = (double *)calloc((size_t)(t->capRows > H ? t->capRows : H) * newW, sizeof(double));
+    for (int r = 0; r < H; r++) memcpy(nm + (size_t)r * newW, t->M + (size_t)r * oldW, sizeof(double) * oldW);
+    free(t->M);
+    t->M = nm;
+    t->W = newW;
+    t->vcol = (int *)realloc(t->vcol, sizeof(int) * newW);
+    if (t->nOpt > 0) {
+        double *no = (double *)calloc((size_t)t->nOpt * newW, sizeof(double));
+        for (int o = 0; o < t->nOpt; o++) memcpy(no + (size_t)o * newW, t->optRC + (size_t)o * oldW, sizeof(double) * oldW);
+        free(t->optRC);
+        t->optRC = no;
+    }
+    free(t->nzc); t->nzc = 0;
+    const int lastColumn = newW - 1;
+    if (optSlot < 0) t->M[lastColumn] = costEntry;
+    else { t->optRC[(size_t)optSlot * newW + lastColumn] = costEntry; t->M[lastColumn] = 0; }
+    ensure_maps(t, varIndex + 1);
+    t->colOf[varIndex] = lastColumn;
+    t->vcol[lastColumn] = varIndex;
+}
+
+/* :304-316 (the stride stays width: the reference only decrements `width`, leaving the matrix layout at the old
+   width -- every later access uses the NEW width as stride, i.e. the reference's tableau is scrambled after this
+   call unless the removed column was the last one; restated literally) */
+int orc_dm_remove_variable(orc_tab *t, int varIndex) {
+    const int W = t->W, lastColumn = W - 1;
+    const int c = orc_dm_take_out_of_base(t, varIndex);
+    if (c < 0) return -2;
+    for (int r = 0; r < t->H; r++) t->M[(size_t)r * W + c] = t->M[(size_t)r * W + lastColumn];
+    t->vcol[c] = t->vcol[lastColumn];
+    t->rowOf[varIndex] = -1;
+    t->colOf[varIndex] = -1;
+    t->W -= 1;
+    return 0;
+}
+
 /* ---- min-heap.ts ---- */
 typedef struct { heap_entry *h; long size, cap, seq; } minheap;
 
@@ -923,6 +1094,7 @@ void orc_get_state(const orc_tab *t, orc_state *s) {
 }
 
 void orc_get_matrix(const orc_tab *t, double *out) { memcpy(out, t->M, sizeof(double) * (size_t)t->H * t->W); }
+void orc_get_flat(const orc_tab *t, double *out, long n) { memcpy(out, t->M, sizeof(double) * (size_t)n); }
 void orc_get_maps(const orc_tab *t, int *vrow, int *vcol) {
     memcpy(vrow, t->vrow, sizeof(int) * t->H);
     memcpy(vcol, t->vcol, sizeof(int) * t->W);

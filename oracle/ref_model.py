@@ -88,11 +88,22 @@ def lib():
                      "orc_get_best_cuts"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_get_maps.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_get_flat.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
         L.orc_row_of.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_row_of.restype = ctypes.c_int
         L.orc_set_flags.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.orc_set_pivot_limit.argtypes = [ctypes.c_void_p, ctypes.c_long]
         L.orc_set_use_mir.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        for name in ("orc_dm_put_in_base", "orc_dm_take_out_of_base", "orc_dm_remove_constraint", "orc_dm_remove_variable"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int]
+            getattr(L, name).restype = ctypes.c_int
+        L.orc_dm_update_rhs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+        L.orc_dm_update_coefficient.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        L.orc_dm_update_coefficient.restype = ctypes.c_int
+        L.orc_dm_update_cost.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        L.orc_dm_add_constraint.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int]
+        L.orc_dm_add_variable.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]
         L.orc_add_mir_cut.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.orc_add_mir_cut.restype = ctypes.c_int
         L.orc_apply_mir_cuts.argtypes = [ctypes.c_void_p]
@@ -627,6 +638,43 @@ class OracleTableau:
         lib().orc_branch_and_cut(self.h)
         return self.state()
 
+    # ---- dynamic-modification.ts (indices instead of Constraint / Variable objects)
+    def put_in_base(self, var_index):
+        return lib().orc_dm_put_in_base(self.h, int(var_index))
+
+    def take_out_of_base(self, var_index):
+        return lib().orc_dm_take_out_of_base(self.h, int(var_index))
+
+    def update_rhs(self, constraint_index, difference):
+        lib().orc_dm_update_rhs(self.h, int(constraint_index), float(difference))
+
+    def update_coefficient(self, constraint_index, var_index, difference):
+        rc = lib().orc_dm_update_coefficient(self.h, int(constraint_index), int(var_index), float(difference))
+        if rc == -1:
+            raise ValueError("[Tableau.updateConstraintCoefficient] constraint index should not be equal to variable index !")
+        return rc
+
+    def update_cost(self, var_index, difference, opt_slot=-1):
+        lib().orc_dm_update_cost(self.h, int(var_index), int(opt_slot), float(difference))
+
+    def add_constraint(self, is_upper, rhs, slack_index, terms):
+        tv = np.ascontiguousarray([v for v, _ in terms], dtype=np.int32)
+        tc = np.ascontiguousarray([c for _, c in terms], dtype=np.float64)
+        lib().orc_dm_add_constraint(self.h, int(bool(is_upper)), float(rhs), int(slack_index), tv.ctypes.data, tc.ctypes.data, len(terms))
+
+    def remove_constraint(self, slack_index):
+        return lib().orc_dm_remove_constraint(self.h, int(slack_index))
+
+    def add_variable(self, var_index, cost_entry, opt_slot=-1):
+        lib().orc_dm_add_variable(self.h, int(var_index), float(cost_entry), int(opt_slot))
+        self.W += 1
+
+    def remove_variable(self, var_index):
+        rc = lib().orc_dm_remove_variable(self.h, int(var_index))
+        if rc == 0:
+            self.W -= 1
+        return rc
+
     def add_mir_cut(self, row, upper=False):   # addLowerBoundMIRCut / addUpperBoundMIRCut
         return bool(lib().orc_add_mir_cut(self.h, int(row), int(bool(upper))))
 
@@ -653,6 +701,12 @@ class OracleTableau:
         s = self.state()
         out = np.empty((s.height, s.width), dtype=np.float64)
         lib().orc_get_matrix(self.h, out.ctypes.data)
+        return out
+
+    def flat(self, n):
+        """The first n doubles of the backing Float64Array, whatever the current width says (removeVariable)."""
+        out = np.empty(n, dtype=np.float64)
+        lib().orc_get_flat(self.h, out.ctypes.data, n)
         return out
 
     def maps(self):

