@@ -416,7 +416,8 @@ napi_value tab_create_comm(napi_env env, napi_callback_info info) {
     return undefined(env);
 }
 
-// branchAndCut({tolerance, isMinimization, checkCycles, maxSpecBatch?, keepSolutions?, timeout?, maxNodes?, shardPolicy?})
+// branchAndCut({tolerance, isMinimization, checkCycles, maxSpecBatch?, keepSolutions?, timeout?, maxNodes?, shardPolicy?,
+//               nodeSelection?, branching?, strongBranchingCandidates?})
 //   == BranchAndCutService.branchAndCut (branch-and-cut.ts:54-199)
 // -> {feasible, bounded, isIntegral, iterations, evaluation, bestPossibleEval, timedOut, bestCuts: BranchCut[],
 //     solutions: [{evaluation, varIndexByRow: Int32Array, rhs: Float64Array}], nodeLps, rounds, pivots, gpuMs}
@@ -436,6 +437,18 @@ napi_value tab_branch_and_cut(napi_env env, napi_callback_info info) {
     opts.timeout_ms = num(env, prop(env, o, "timeout"));
     opts.max_nodes = (int64_t)num(env, prop(env, o, "maxNodes"));
     opts.shard_policy = (int32_t)num(env, prop(env, o, "shardPolicy"));
+    {   // options.nodeSelection / options.branching select the enhanced service (main.ts:62-83)
+        char ns[16] = {0}, br[20] = {0};
+        size_t len = 0;
+        if (!is_nullish(env, prop(env, o, "nodeSelection"))) napi_get_value_string_utf8(env, prop(env, o, "nodeSelection"), ns, sizeof(ns), &len);
+        if (!is_nullish(env, prop(env, o, "branching"))) napi_get_value_string_utf8(env, prop(env, o, "branching"), br, sizeof(br), &len);
+        if (ns[0] || br[0] || truthy(env, prop(env, o, "enhanced"))) {
+            opts.service = 1;
+            opts.node_selection = !std::strcmp(ns, "best-first") ? 1 : !std::strcmp(ns, "depth-first") ? 2 : 3;
+            opts.branching = !std::strcmp(br, "most-fractional") ? 1 : !std::strcmp(br, "strong") ? 3 : 2;
+            opts.strong_candidates = (int32_t)num(env, prop(env, o, "strongBranchingCandidates"));
+        }
+    }
     opts.rank = box->rank;
     opts.n_ranks = box->comm ? box->n_ranks : 1;
     opts.comm = box->comm;

@@ -12,6 +12,21 @@ import type { BranchAndCutService } from "./branch-and-cut";
 import { createBranchAndCutService } from "./branch-and-cut";
 import GpuTableau from "./gpu-tableau";
 
+/** The enhanced service (enhanced-branch-and-cut.ts) on the device tableau: same options object as
+ *  createEnhancedBranchAndCutService; main.ts:62-83 returns it when options.nodeSelection / options.branching are set. */
+export function createGpuEnhancedBranchAndCutService(options: {
+    nodeSelection?: "best-first" | "depth-first" | "hybrid";
+    branching?: "most-fractional" | "pseudocost" | "strong";
+    strongBranchingCandidates?: number;
+} = {}): BranchAndCutService {
+    const strategy = { enhanced: true, nodeSelection: options.nodeSelection ?? "hybrid", branching: options.branching ?? "pseudocost",
+                       strongBranchingCandidates: options.strongBranchingCandidates ?? 5 };
+    return {
+        applyCuts(tableau: Tableau, cuts: BranchCut[]): void { (tableau as GpuTableau).applyCuts(cuts); },
+        branchAndCut(tableau: Tableau): void { (tableau as GpuTableau).runBranchAndCut(strategy); },
+    };
+}
+
 export function createGpuBranchAndCutService(): BranchAndCutService {
     const host = createBranchAndCutService();
     return {

@@ -128,7 +128,7 @@ export default class GpuTableau extends Tableau {
         this.nVars = this.width + this.height - 2 + branchingCuts.length;  // cutting-strategies.ts:34,70 (kept as is)
     }
     applyCuts(branchingCuts: BranchCut[]): void {
-        if (this.model?.useMIRCuts) { super.applyCuts(branchingCuts); return; }  // host MIR loop: see INTEGRATION.md
+        this.tab().setOption(13 /* JSLP_OPT_USE_MIR_CUTS */, this.model?.useMIRCuts ? 1 : 0);  // MIR loop runs on the device
         const first = this.lastElementIndex;
         this.absorb(this.tab().applyCuts(branchingCuts, this.checkCycles()));
         for (let h = 0; h < branchingCuts.length; h++) this.variablesPerIndex[first + h] = new SlackVariable("s" + (first + h), first + h);
@@ -139,11 +139,16 @@ export default class GpuTableau extends Tableau {
     getMostFractionalVar(): VariableValue { return this.tab().mostFractional(); }
 
     // ---- tableau.ts:244-246: the whole loop of branch-and-cut.ts:54-199 runs behind one call
-    branchAndCut(): void {
+    branchAndCut(): void { this.runBranchAndCut({}); }
+
+    /** `strategy` = {nodeSelection?, branching?, strongBranchingCandidates?} runs the enhanced service's loop
+     *  (enhanced-branch-and-cut.ts:223-434) instead; see createGpuEnhancedBranchAndCutService. */
+    runBranchAndCut(strategy: Record<string, unknown>): void {
         const model = this.model!;
+        if (model.useMIRCuts) this.tab().setOption(13 /* JSLP_OPT_USE_MIR_CUTS */, 1);
         const r = this.tab().branchAndCut({
             tolerance: model.tolerance ?? 0, isMinimization: model.isMinimization, checkCycles: model.checkForCycles,
-            keepSolutions: model.keep_solutions === true, timeout: model.timeout ?? 0,
+            keepSolutions: model.keep_solutions === true, timeout: model.timeout ?? 0, ...strategy,
         });
         this.feasible = r.feasible; this.bounded = r.bounded; this.evaluation = r.evaluation;
         this.bestPossibleEval = r.bestPossibleEval; this.branchAndCutIterations = r.iterations;

@@ -39,7 +39,8 @@ class BnbOpts(C.Structure):
                 ("max_spec_batch", C.c_int32), ("rank", C.c_int32), ("n_ranks", C.c_int32),
                 ("max_nodes", C.c_int64), ("all_gather", ALL_GATHER_FN), ("user", C.c_void_p),
                 ("comm", C.c_void_p), ("shard_policy", C.c_int32), ("keep_solutions", C.c_int32),
-                ("timeout_ms", C.c_double)]
+                ("timeout_ms", C.c_double), ("service", C.c_int32), ("node_selection", C.c_int32),
+                ("branching", C.c_int32), ("strong_candidates", C.c_int32)]
 
 
 class BnbStatus(C.Structure):

@@ -1335,4 +1335,5 @@ extern "C" int jslp_pivot_log(jslp_tab *t, int32_t *entries, int cap, int *n) {
 
 #include "jslp_dynamic.cuh"
 #include "jslp_comm.cuh"
+#include "jslp_bnb_enhanced.cuh"
 #include "jslp_bnb.cuh"

@@ -29,11 +29,13 @@ class Solver:
             if model.get("external"):
                 raise NotImplementedError("external solvers (src/external) are out of scope")
             options = model.get("options") or {}
-            if options.get("nodeSelection") or options.get("branching") or options.get("useIncremental") is True:
+            if options.get("useIncremental") is True:
                 raise NotImplementedError(
-                    "enhanced / incremental branch-and-cut services are opt-in reference paths outside the "
-                    "GPU hot-path scope (SURVEY.md 8f.3)")
+                    "the incremental branch-and-cut service (experimental, opt-in; it re-solves from parent checkpoints, "
+                    "so its numerics differ from every other path) is outside the GPU hot-path scope (SURVEY.md 8f.3)")
             instance = Model(precision).loadJson(model)
+            if options.get("nodeSelection") or options.get("branching"):  # selectBranchAndCutService, main.ts:62-83
+                instance.branchAndCutOptions = {"nodeSelection": options.get("nodeSelection"), "branching": options.get("branching")}
         else:
             instance = model
         instance.tableau.engine = self.engine

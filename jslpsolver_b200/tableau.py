@@ -424,6 +424,11 @@ class GpuTableau:
                 else:
                     opts.all_gather, keep = D.make_all_gather_hook()
         opts.shard_policy = int(self.shard_policy)
+        sel = getattr(m, "branchAndCutOptions", None)  # main.ts:62-83: options.nodeSelection / options.branching
+        if sel:
+            opts.service = 1
+            opts.node_selection = {"best-first": 1, "depth-first": 2, "hybrid": 3}[sel.get("nodeSelection") or "hybrid"]
+            opts.branching = {"most-fractional": 1, "pseudocost": 2, "strong": 3}[sel.get("branching") or "pseudocost"]
         opts.max_nodes = int(getattr(m, "max_nodes", 0) or 0)
         # model.timeout [ms] and options.keep_solutions (model.ts:338-374; branch-and-cut.ts:61-63,76,143-153)
         opts.timeout_ms = float(getattr(m, "timeout", 0) or 0)

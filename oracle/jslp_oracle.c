@@ -17,6 +17,7 @@
  *   cutting-strategies.ts:16-72 addCutConstraints -> orc_add_cuts
  *   cutting-strategies.ts:74-212 addLowerBoundMIRCut / addUpperBoundMIRCut / applyMIRCuts -> orc_add_mir_cut / orc_apply_mir_cuts
  *   mip-utils.ts:67-98  computeFractionalVolume -> orc_fractional_volume
+ *   enhanced-branch-and-cut.ts:54-437  createEnhancedBranchAndCutService -> orc_enhanced_branch_and_cut
  *   dynamic-modification.ts:16-316 putInBase / takeOutOfBase / updateRightHandSide / updateConstraintCoefficient /
  *                       updateCost / addConstraint / removeConstraint / addVariable / removeVariable -> orc_dm_*
  *   mip-utils.ts:43-61,100-126  isIntegral / getMostFractionalVar
@@ -1071,6 +1072,218 @@ done:
     for (long i = 0; i < hp.size; i++) free_branch(hp.h[i].branch);
     free(hp.h);
     free(bestOpt);
+}
+
+/* ---- enhanced-branch-and-cut.ts ---- */
+typedef struct { double upSum, downSum; long upCount, downCount; } pseudo_cost;
+typedef struct { int index; double value, fraction; } frac_cand;
+
+/* :94-108 */
+static double pc_score(const pseudo_cost *d, double fraction) {
+    const double upPseudo = d->upCount > 0 ? d->upSum / d->upCount : 1;
+    const double downPseudo = d->downCount > 0 ? d->downSum / d->downCount : 1;
+    const double upEstimate = upPseudo * (1 - fraction);
+    const double downEstimate = downPseudo * fraction;
+    const double a = upEstimate > 1e-6 ? upEstimate : (upEstimate != upEstimate ? upEstimate : 1e-6);     /* Math.max(x, 1e-6) */
+    const double b = downEstimate > 1e-6 ? downEstimate : (downEstimate != downEstimate ? downEstimate : 1e-6);
+    return a * b;
+}
+
+/* stable insertion sort by fraction descending == Array.prototype.sort((a, b) => b.fraction - a.fraction) */
+static void sort_by_fraction_desc(frac_cand *c, int n) {
+    for (int i = 1; i < n; i++) {
+        frac_cand x = c[i];
+        int j = i - 1;
+        while (j >= 0 && c[j].fraction < x.fraction) { c[j + 1] = c[j]; j--; }
+        c[j + 1] = x;
+    }
+}
+
+/* :110-195; branching: 1 = most-fractional, 2 = pseudocost, 3 = strong.  Returns var index or -1. */
+static int enh_select_branching_variable(orc_tab *t, pseudo_cost *pc, int branching, int strongCandidates, double *val) {
+    frac_cand *cand = (frac_cand *)malloc(sizeof(frac_cand) * (size_t)(t->nInt > 0 ? t->nInt : 1));
+    int n = 0;
+    for (int v = 0; v < t->nInt; v++) {
+        const int varIndex = t->intVars[v];
+        const int row = t->rowOf[varIndex];
+        if (row != -1) {
+            const double value = t->M[(size_t)row * t->W];
+            const double fraction = fabs(value - js_round(value));
+            if (fraction > t->precision) { cand[n].index = varIndex; cand[n].value = value; cand[n].fraction = fraction; n++; }
+        }
+    }
+    int sel = -1;
+    if (n > 0) {
+        frac_cand best = cand[0];
+        if (branching == 1) {
+            sort_by_fraction_desc(cand, n);
+            best = cand[0];
+        } else if (branching == 2) {
+            double bestScore = -INFINITY;
+            for (int i = 0; i < n; i++) {
+                const double score = pc_score(&pc[cand[i].index], cand[i].fraction);
+                if (score > bestScore) { bestScore = score; best = cand[i]; }
+            }
+        } else if (branching == 3) {
+            sort_by_fraction_desc(cand, n);
+            if (n > strongCandidates) n = strongCandidates;
+            double bestScore = -INFINITY;
+            best = cand[0];
+            for (int i = 0; i < n; i++) {
+                const pseudo_cost *d = &pc[cand[i].index];
+                double score;
+                if (d->upCount >= 2 && d->downCount >= 2) score = pc_score(d, cand[i].fraction);
+                else score = cand[i].fraction * (1 - cand[i].fraction);
+                if (score > bestScore) { bestScore = score; best = cand[i]; }
+            }
+        }
+        sel = best.index;
+        *val = best.value;
+    }
+    free(cand);
+    return sel;
+}
+
+/* :197-221 */
+static void enh_apply_cuts(orc_tab *t, const orc_cut *cuts, int n) {
+    orc_restore(t);
+    orc_add_cuts(t, cuts, n);
+    orc_simplex(t);
+    if (t->useMIR && t->feasible) {
+        int improved = 1, mirIterations = 0;
+        const int maxMIRIterations = 3;
+        while (improved && mirIterations < maxMIRIterations) {
+            const double before = orc_fractional_volume(t, 1);
+            orc_apply_mir_cuts(t);
+            orc_simplex(t);
+            const double after = orc_fractional_volume(t, 1);
+            mirIterations++;
+            if (after >= 0.9 * before) improved = 0;
+        }
+    }
+}
+
+/* :223-434.  nodeSelection: 1 = best-first, 2 = depth-first, 3 = hybrid; branching as above.  One service instance per
+ * call (main.ts:62-83 creates a fresh one per Solve), so the pseudocosts start empty. */
+void orc_enhanced_branch_and_cut(orc_tab *t, int nodeSelection, int branching, int strongCandidates) {
+    minheap hp = {0, 0, 0, 0};
+    orc_branch **stack = 0;
+    long sp = 0, scap = 0;
+    int iterations = 0;
+    const double tolerance = t->tolerance;
+    int toleranceFlag = 1;
+    double bestEvaluation = INFINITY;
+    orc_branch *bestBranch = 0;
+    const int nOpt = t->nOpt;
+    double *bestOpt = (double *)malloc(sizeof(double) * (nOpt > 0 ? nOpt : 1));
+    for (int o = 0; o < nOpt; o++) bestOpt[o] = INFINITY;
+    const int pcN = t->mapCap + 64;
+    pseudo_cost *pc = (pseudo_cost *)calloc((size_t)pcN, sizeof(pseudo_cost));
+    const int switchToBestFirstAfterSolutions = 1;
+    int solutionsFound = 0;
+    int useDepthFirst = nodeSelection == 2 || nodeSelection == 3;
+#define STACK_PUSH(b) do { if (sp == scap) { scap = scap ? scap * 2 : 64; stack = (orc_branch **)realloc(stack, sizeof(orc_branch *) * scap); } stack[sp++] = (b); } while (0)
+    if (useDepthFirst) STACK_PUSH(make_branch(-INFINITY, 0)); else heap_push(&hp, make_branch(-INFINITY, 0));
+
+    while ((useDepthFirst ? sp > 0 : hp.size > 0) && toleranceFlag) {
+        if (t->maxNodes > 0 && iterations >= t->maxNodes) break;
+        const double acceptableThreshold = t->isMin ? t->bestPossibleEval * (1 + tolerance) : t->bestPossibleEval * (1 - tolerance);
+        if (tolerance > 0 && bestEvaluation < acceptableThreshold) toleranceFlag = 0;
+        orc_branch *active;
+        if (useDepthFirst && sp > 0) active = stack[--sp];
+        else if (hp.size > 0) active = heap_pop(&hp);
+        else break;
+        if (active->relaxedEvaluation > bestEvaluation) { free_branch(active); continue; }
+        const double parentEval = t->evaluation;
+        const long pivBefore = t->totalPivots;
+        enh_apply_cuts(t, active->cuts, active->nCuts);
+        iterations++;
+        double *nl = 0;
+        if (t->nlog && t->nlogN < t->nlogCap) {
+            nl = t->nlog + 8 * t->nlogN++;
+            nl[0] = iterations; nl[1] = active->nCuts; nl[2] = t->feasible;
+            nl[3] = t->evaluation; nl[4] = -1; nl[5] = -1; nl[6] = 0;
+            nl[7] = (double)(t->totalPivots - pivBefore);
+        }
+        if (!t->feasible) { free_branch(active); continue; }
+        const double evaluation = t->evaluation;
+        if (evaluation > bestEvaluation) { free_branch(active); continue; }
+        if (active->nCuts > 0 && parentEval != 0) {  /* :281-294 */
+            const orc_cut lastCut = active->cuts[active->nCuts - 1];
+            const double improvement = fabs(evaluation - parentEval);
+            const double fraction = 0.5;
+            if (lastCut.varIndex >= 0 && lastCut.varIndex < pcN) {
+                pseudo_cost *d = &pc[lastCut.varIndex];
+                const int up = lastCut.type == 0;
+                const double normalizedImprovement = improvement / (up ? 1 - fraction : fraction);
+                if (up) { d->upSum += normalizedImprovement; d->upCount++; }
+                else { d->downSum += normalizedImprovement; d->downCount++; }
+            }
+        }
+        if (evaluation == bestEvaluation) {
+            int worse = 1;
+            for (int o = 0; o < nOpt; o++) {
+                const double v = t->optRC[(size_t)o * t->W];
+                if (v > bestOpt[o]) break;
+                else if (v < bestOpt[o]) { worse = 0; break; }
+            }
+            if (worse) { free_branch(active); continue; }
+        }
+        if (orc_is_integral(t)) {
+            if (nl) nl[4] = 1;
+            t->isIntegralFlag = 1;
+            solutionsFound++;
+            if (iterations == 1) { t->bncIterations = iterations; free_branch(active); goto done; }
+            if (bestBranch) free_branch(bestBranch);
+            bestBranch = active;
+            bestEvaluation = evaluation;
+            for (int o = 0; o < nOpt; o++) bestOpt[o] = t->optRC[(size_t)o * t->W];
+            if (nodeSelection == 3 && solutionsFound >= switchToBestFirstAfterSolutions) {
+                useDepthFirst = 0;
+                while (sp > 0) heap_push(&hp, stack[--sp]);
+            }
+        } else {
+            if (nl) nl[4] = 0;
+            if (iterations == 1) orc_save(t);
+            double varValue = 0;
+            const int varIndex = enh_select_branching_variable(t, pc, branching, strongCandidates, &varValue);
+            if (varIndex < 0) { free_branch(active); continue; }
+            if (nl) { nl[5] = varIndex; nl[6] = varValue; }
+            orc_branch *high = make_branch(evaluation, active->nCuts + 1);
+            orc_branch *low = make_branch(evaluation, active->nCuts + 1);
+            for (int c = 0; c < active->nCuts; c++) {
+                const orc_cut cut = active->cuts[c];
+                if (cut.varIndex == varIndex) {
+                    if (cut.type == 0) low->cuts[low->nCuts++] = cut;
+                    else high->cuts[high->nCuts++] = cut;
+                } else {
+                    high->cuts[high->nCuts++] = cut;
+                    low->cuts[low->nCuts++] = cut;
+                }
+            }
+            orc_cut ch = {0, varIndex, ceil(varValue)};
+            orc_cut cl = {1, varIndex, floor(varValue)};
+            high->cuts[high->nCuts++] = ch;
+            low->cuts[low->nCuts++] = cl;
+            if (useDepthFirst) { STACK_PUSH(low); STACK_PUSH(high); }
+            else { heap_push(&hp, high); heap_push(&hp, low); }
+            free_branch(active);
+        }
+    }
+    if (bestBranch) {
+        enh_apply_cuts(t, bestBranch->cuts, bestBranch->nCuts);
+        free(t->bestCuts);
+        t->bestCuts = (orc_cut *)malloc(sizeof(orc_cut) * (bestBranch->nCuts > 0 ? bestBranch->nCuts : 1));
+        memcpy(t->bestCuts, bestBranch->cuts, sizeof(orc_cut) * bestBranch->nCuts);
+        t->nBestCuts = bestBranch->nCuts;
+        free_branch(bestBranch);
+    }
+    t->bncIterations = iterations;
+done:
+    for (long i = 0; i < hp.size; i++) free_branch(hp.h[i].branch);
+    for (long i = 0; i < sp; i++) free_branch(stack[i]);
+    free(hp.h); free(stack); free(bestOpt); free(pc);
+#undef STACK_PUSH
 }
 
 /* ---- read-back ---- */

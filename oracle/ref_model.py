@@ -94,6 +94,8 @@ def lib():
         L.orc_set_flags.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.orc_set_pivot_limit.argtypes = [ctypes.c_void_p, ctypes.c_long]
         L.orc_set_use_mir.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_enhanced_branch_and_cut.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.orc_enhanced_branch_and_cut.restype = None
         for name in ("orc_dm_put_in_base", "orc_dm_take_out_of_base", "orc_dm_remove_constraint", "orc_dm_remove_variable"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int]
             getattr(L, name).restype = ctypes.c_int
@@ -638,6 +640,13 @@ class OracleTableau:
         lib().orc_branch_and_cut(self.h)
         return self.state()
 
+    NODE_SELECTION = {"best-first": 1, "depth-first": 2, "hybrid": 3}
+    BRANCHING = {"most-fractional": 1, "pseudocost": 2, "strong": 3}
+
+    def enhanced_branch_and_cut(self, node_selection="hybrid", branching="pseudocost", strong_candidates=5):
+        lib().orc_enhanced_branch_and_cut(self.h, self.NODE_SELECTION[node_selection], self.BRANCHING[branching], strong_candidates)
+        return self.state()
+
     # ---- dynamic-modification.ts (indices instead of Constraint / Variable objects)
     def put_in_base(self, var_index):
         return lib().orc_dm_put_in_base(self.h, int(var_index))
@@ -790,8 +799,14 @@ def solve_full(jm: dict, precision=None, fast_cycles=False, pivot_log=0, node_lo
                         is_min=model.isMinimization, tolerance=model.tolerance or 0.0,
                         max_nodes=max_nodes, pivot_log=pivot_log, node_log=node_log, use_mir=bool(model.useMIRCuts))
     sol.tableau = tab
-    if ints:  # tableau.ts:250-258
-        st = tab.branch_and_cut()
+    if ints:  # tableau.ts:250-258; the service is chosen from model.options (main.ts:62-83)
+        options = jm.get("options") or {}
+        if options.get("useIncremental") is True:
+            raise NotImplementedError("incremental branch-and-cut service (experimental, opt-in) is not restated")
+        if js_truthy(options.get("nodeSelection")) or js_truthy(options.get("branching")):
+            st = tab.enhanced_branch_and_cut(options.get("nodeSelection") or "hybrid", options.get("branching") or "pseudocost")
+        else:
+            st = tab.branch_and_cut()
         sol.iter = st.bncIterations
     else:
         st = tab.simplex()

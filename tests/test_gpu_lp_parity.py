@@ -533,3 +533,37 @@ def test_model_level_edits_after_solve():
     m.removeConstraint(extra)                         # removeConstraint
     s4 = m.solve()
     assert s4.feasible and s4.evaluation >= s2.evaluation - 1e-6
+
+
+# ------------------------------------------------------------------ enhanced service (enhanced-branch-and-cut.ts)
+ENHANCED = [{"nodeSelection": "hybrid"}, {"nodeSelection": "depth-first", "branching": "strong"},
+            {"nodeSelection": "best-first", "branching": "most-fractional"}, {"branching": "pseudocost", "useMIRCuts": True}]
+
+
+@pytest.mark.parametrize("opts", ENHANCED, ids=lambda o: "-".join(str(v) for v in o.values()))
+@pytest.mark.parametrize("fx", [f for f in BUNDLE["fixtures"] if (f["model"].get("ints") or f["model"].get("binaries"))],
+                         ids=lambda f: f["file"])
+def test_enhanced_service_matches_oracle(fx, opts):
+    """options.nodeSelection / options.branching select the enhanced service (main.ts:62-83): same node sequence (stack /
+    heap order, pseudocost-driven branching variables), same final tableau as the oracle's restatement."""
+    import jslpsolver_b200 as J
+    from oracle import ref_model
+    if fx["file"] in ("Vendor Selection.json", "Monster_II.json") and "branching" in opts and opts.get("nodeSelection") != "depth-first":
+        pytest.skip("long MIP: covered by two combinations")
+    jm = strip_timeouts(fx["model"])
+    jm["options"] = dict(jm.get("options") or {}, **opts)
+    osol = ref_model.solve_full(jm, fast_cycles=True, node_log=1 << 20)
+    if osol.tableau is None:
+        pytest.skip("decided by presolve")
+    s = J.Solver()
+    gsol = s.Solve(jm, full=True)
+    gt = gsol._tableau
+    onl, gnl = osol.tableau.node_log(), gt.node_log()
+    assert gnl.shape == onl.shape, (gnl.shape, onl.shape)
+    for i in range(len(onl)):
+        a, b = gnl[i], onl[i]
+        ok = all(a[k] == b[k] for k in (0, 1, 2, 4, 5, 7)) and same_bits(a[6], b[6]) and (not b[2] or same_bits(a[3], b[3]))
+        assert ok, f"node {i}: gpu={a.tolist()} oracle={b.tolist()}"
+    assert gt.branchAndCutIterations == osol.state.bncIterations
+    assert same_bits(gt.matrix2d(), osol.tableau.matrix())
+    assert s._simplified(gsol) == ref_model.simplify(osol)

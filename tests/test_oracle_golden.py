@@ -248,3 +248,28 @@ def test_dynamic_modification_known_answers():
     t = _dm_tableau([[0.0, 0, 0, 0], [1.0, 0, 2, 0], [1.0, 5, 3, 0]], [-1, 1, 2], [-1, 3, 4, 5], precision=1e-9)
     assert t.put_in_base(1) == 1 and t.put_in_base(3) == 2 and t.maps()[0][2] == 3
     assert t.take_out_of_base(4) == 2 and t.take_out_of_base(1) == 2   # row 1's first non-zero column is 2
+
+
+# ------------------------------------------------------------------ enhanced service (enhanced-branch-and-cut.ts)
+def test_enhanced_service_known_answers():
+    """solver.options.test.ts:139-250: every nodeSelection / branching choice is feasible, and all node-selection
+    strategies reach the same optimum; on the MIP fixtures without a tolerance every combination keeps the optimum."""
+    base = {"optimize": "profit", "opType": "max", "constraints": {"capacity": {"max": 50}, "labor": {"max": 40}},
+            "variables": {"table": {"profit": 12, "capacity": 3, "labor": 5}, "chair": {"profit": 8, "capacity": 2, "labor": 3}},
+            "ints": {"table": 1, "chair": 1}}
+    results = [ref_model.Solve(dict(base, options={"nodeSelection": ns})) for ns in ("best-first", "depth-first", "hybrid")]
+    assert all(r["feasible"] and r["result"] > 0 for r in results)
+    assert results[0]["result"] == results[1]["result"] == results[2]["result"] == ref_model.Solve(base)["result"]
+    knap = {"optimize": "value", "opType": "max", "constraints": {"weight": {"max": 100}},
+            "variables": {"item1": {"value": 60, "weight": 10}, "item2": {"value": 100, "weight": 20}, "item3": {"value": 120, "weight": 30}},
+            "ints": {"item1": 1, "item2": 1, "item3": 1}}
+    for br in ("most-fractional", "pseudocost", "strong"):
+        assert ref_model.Solve(dict(knap, options={"branching": br}))["feasible"]
+    for fx in BUNDLE["fixtures"]:
+        m = strip_timeouts(fx["model"])
+        if not (m.get("ints") or m.get("binaries")) or m.get("tolerance") or (m.get("options") or {}).get("tolerance"):
+            continue
+        for opts in ({"nodeSelection": "hybrid"}, {"nodeSelection": "depth-first", "branching": "strong"}, {"branching": "most-fractional"}):
+            r = ref_model.Solve(dict(m, options=dict(m.get("options") or {}, **opts)), fast_cycles=True)
+            bad = [b for b in compare_solutions(r, fx["expects"]) if b.startswith(("result", "feasible"))]
+            assert not bad, (fx["file"], opts, bad)
