@@ -162,7 +162,7 @@ struct jslp_tab {
     int *d_count = nullptr, *h_count = nullptr;
     int node_slots = -1;    // JSLP_OPT_NODE_SLOTS: -1 = auto, 0 = off (one node at a time), n = at most n slots
     int slot_steps = 32;    // pivots per slot per host poll
-    int slot_variant = 11;  // kernel instantiation of the slot batch (flat streaming: the batch is HBM-bound)
+    int slot_variant = 12;  // kernel instantiation of the slot batch: flat streaming, 3 CTAs per SM (more row CTAs per slot)
     long long node_kernel_ns = 0;  // sum over rounds of the slowest node CTA (reporting)
 };
 
@@ -556,12 +556,12 @@ static const int N_STEP_VARIANTS = (int)(sizeof(STEP_VARIANTS) / sizeof(STEP_VAR
 static int n_step_variants() { return N_STEP_VARIANTS; }
 static const int SMALL_BATCH = 24;  // steps in the first graph of a solve
 
-// Auto: while the ping-pong pair fits L2 (126 MB; measured: up to 2 x 32 MB at 2001^2) the per-row loop with
-// prefetch is fastest; once the pair spills to HBM the flat loop with 8 + 8 loads in flight per thread wins
-// (dense 3000^2: 26.8 vs 31.1 us per pivot, profiles/r02_variants.md).
+// Auto: while the buffer being WRITTEN fits L2 with room to spare (the dead-load hint keeps it there: up to a pair of
+// about the L2 size) the per-row loop with prefetch is fastest; beyond that the flat loop with 8 + 8 loads in flight
+// per thread wins (dense 2500^2: 14.9 vs 15.9 us per pivot; dense 3000^2: 24.2 vs 20.1; profiles/r02_variants.md).
 static int variant_index(const jslp_tab *t) {
     if (t->variant >= 0) return t->variant;
-    return 16.0 * (double)t->rowcap * t->stride > 0.62 * (double)t->ctx->l2_bytes ? 11 : 1;
+    return 16.0 * (double)t->rowcap * t->stride > 0.95 * (double)t->ctx->l2_bytes ? 11 : 1;
 }
 static const StepVariant &step_variant(const jslp_tab *t) { return STEP_VARIANTS[variant_index(t)]; }
 

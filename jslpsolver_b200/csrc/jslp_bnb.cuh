@@ -94,9 +94,10 @@ static int slots_for(const jslp_tab *t, int rowcap, int want) {
     }
     int cap = geom;
     if (t->node_slots > 0) cap = std::min(cap, t->node_slots);
-    else {  // auto: keep the ping-pong pairs of all slots inside L2 (each pivot re-reads what the last one wrote)
-        const double pair_bytes = 16.0 * (double)rowcap * t->stride;
-        const int l2 = (int)std::floor(0.85 * (double)t->ctx->l2_bytes / pair_bytes);
+    else {  // auto: the buffers being WRITTEN by all slots (half of each pair; the dead-load hint lets L2 drop the other
+            // half first) should stay in L2: each pivot re-reads what the last one wrote
+        const double live_bytes = 8.0 * (double)rowcap * t->stride;
+        const int l2 = (int)std::floor(0.55 * (double)t->ctx->l2_bytes / live_bytes);
         cap = std::min(cap, std::max(2, l2));
     }
     return std::min(cap, want) >= 2 ? std::min(cap, want) : 0;

@@ -753,6 +753,16 @@ __device__ __forceinline__ double2 ld_v2(const double *p) {
     asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// Load of a tableau entry that is DEAD after this read: the ping-pong step reads buffer M once per launch and never
+// again (the next launch reads what this one writes to M2), so these lines should be the first to leave L2.  With
+// L1::no_allocate loads (SASS LDG.E.NA) and plain stores the 126 MB L2 keeps the WRITTEN buffer instead of both: a
+// ping-pong copy holds 8.0-8.7 TB/s up to 2 x 75 MB instead of dropping to 5.5 TB/s beyond 2 x 40 MB
+// (scripts/micro/copybw.cu, profiles/r02_copy_flavours.md).
+__device__ __forceinline__ double2 ld_v2_dead(const double *p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void st_v2(double *p, double2 v) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }

@@ -317,7 +317,7 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
                 double2 old[RC];
 #pragma unroll
                 for (int j = 0; j < RC; j++)
-                    if (valid[j] && !isp[j]) old[j] = ld_v2(sb + j * stride + 2 * c2);
+                    if (valid[j] && !isp[j]) old[j] = ld_v2_dead(sb + j * stride + 2 * c2);
                 emit(c2, frow2[c2], old);
             }
         } else {  // software prefetch: the next pair's RC loads are in flight while this pair is stored
@@ -326,7 +326,7 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
             if (c2 < npair) {
 #pragma unroll
                 for (int j = 0; j < RC; j++)
-                    if (valid[j] && !isp[j]) old[j] = ld_v2(sb + j * stride + 2 * c2);
+                    if (valid[j] && !isp[j]) old[j] = ld_v2_dead(sb + j * stride + 2 * c2);
             }
             while (c2 < npair) {
                 const int n2 = c2 + NT;
@@ -334,7 +334,7 @@ __device__ __forceinline__ void update_rows_pp(const double *src, double *dst, i
                 if (n2 < npair) {
 #pragma unroll
                     for (int j = 0; j < RC; j++)
-                        if (valid[j] && !isp[j]) oldn[j] = ld_v2(sb + j * stride + 2 * n2);
+                        if (valid[j] && !isp[j]) oldn[j] = ld_v2_dead(sb + j * stride + 2 * n2);
                 }
                 emit(c2, frow2[c2], old);
                 c2 = n2;
@@ -368,13 +368,13 @@ __device__ __forceinline__ void update_rows_pp_flat(const double *src, double *d
 #pragma unroll
     for (int j = 0; j < K; j++) {
         const int idx = tid + j * NT;
-        if (idx < total) cur[j] = ld_v2(sb + 2 * (size_t)idx);
+        if (idx < total) cur[j] = ld_v2_dead(sb + 2 * (size_t)idx);
     }
     for (int i0 = tid; i0 < total; i0 += K * NT) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int idx = i0 + (K + j) * NT;
-            if (idx < total) nxt[j] = ld_v2(sb + 2 * (size_t)idx);
+            if (idx < total) nxt[j] = ld_v2_dead(sb + 2 * (size_t)idx);
         }
 #pragma unroll
         for (int j = 0; j < K; j++) {
