@@ -1,4 +1,10 @@
 set -u
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest.log 2>&1; echo "pytest exit $?"; tail -n 8 gpurun_out/pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r02b.json 2> gpurun_out/bench_r02b.err; echo "bench exit $?"; cat gpurun_out/bench_r02b.json | cut -c1-3000; tail -3 gpurun_out/bench_r02b.err
+for gps in 1 2; do
+GRID_PER_SM=$gps VARIANTS=1 SHAPES=dense300,dense600,dense800,dense1200,dense1400,dense1500 timeout 600 python scripts/variant_bench.py 2>&1 | python -c "
+import sys, json
+rows = [json.loads(l) for l in sys.stdin if l.startswith('{')]
+best = {}
+for r in rows: best[r['shape']] = min(best.get(r['shape'], 1e9), r['us_per_pivot'])
+print('grid_per_sm', $gps, best)
+"
+done

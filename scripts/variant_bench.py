@@ -26,6 +26,7 @@ for shape in shapes:
     for v in variants + variants[:1]:
         g.set_option(_lib.OPT_ENGINE, 2)
         g.set_option(_lib.OPT_STEP_VARIANT, v)
+        g.set_option(_lib.OPT_GRID_PER_SM, int(os.environ.get("GRID_PER_SM", "0")))
         g.restore()
         g.simplex()
         st = g.lastStatus
@@ -33,5 +34,5 @@ for shape in shapes:
         key = (piv, st.evaluation_raw)
         ref = ref or key
         print(json.dumps({"shape": shape, "variant": v, "pivots": piv, "gpu_ms": round(st.gpu_ms, 2),
-                          "us_per_pivot": round(1e3 * st.gpu_ms / max(1, piv), 3), "same_as_first": key == ref}), flush=True)
+                          "us_per_pivot": round(1e3 * st.gpu_ms / max(1, piv), 3), "grid_per_sm": os.environ.get("GRID_PER_SM", "0"), "same_as_first": key == ref}), flush=True)
     g.close()
