@@ -501,6 +501,100 @@ napi_value tab_branch_and_cut(napi_env env, napi_callback_info info) {
     return r;
 }
 
+// ---- dynamic-modification.ts on the device tableau: constraints / variables named by their element index
+napi_value tab_put_in_base(napi_env env, napi_callback_info info) {       // putInBase(varIndex) -> row
+    size_t argc = 1;
+    napi_value argv[1];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    int r = -1;
+    if (!box || throw_if(env, jslp_put_in_base(box->tab, (int)num(env, argv[0]), &r))) return nullptr;
+    napi_value v;
+    napi_create_int32(env, r, &v);
+    return v;
+}
+napi_value tab_take_out_of_base(napi_env env, napi_callback_info info) {  // takeOutOfBase(varIndex) -> column
+    size_t argc = 1;
+    napi_value argv[1];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    int c = -1;
+    if (!box || throw_if(env, jslp_take_out_of_base(box->tab, (int)num(env, argv[0]), &c))) return nullptr;
+    napi_value v;
+    napi_create_int32(env, c, &v);
+    return v;
+}
+napi_value tab_update_rhs(napi_env env, napi_callback_info info) {        // updateRightHandSide(constraintIndex, difference)
+    size_t argc = 2;
+    napi_value argv[2];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    if (!box || throw_if(env, jslp_update_rhs(box->tab, (int)num(env, argv[0]), num(env, argv[1])))) return nullptr;
+    return undefined(env);
+}
+napi_value tab_update_coefficient(napi_env env, napi_callback_info info) {  // (constraintIndex, varIndex, difference)
+    size_t argc = 3;
+    napi_value argv[3];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    if (!box || throw_if(env, jslp_update_coefficient(box->tab, (int)num(env, argv[0]), (int)num(env, argv[1]), num(env, argv[2])))) return nullptr;
+    return undefined(env);
+}
+napi_value tab_update_cost(napi_env env, napi_callback_info info) {       // (varIndex, optSlot, difference)
+    size_t argc = 3;
+    napi_value argv[3];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    if (!box || throw_if(env, jslp_update_cost(box->tab, (int)num(env, argv[0]), (int)num(env, argv[1], -1), num(env, argv[2])))) return nullptr;
+    return undefined(env);
+}
+napi_value tab_add_constraint(napi_env env, napi_callback_info info) {    // (isUpperBound, rhs, slackIndex, termVars: Int32Array, termCoefs: Float64Array)
+    size_t argc = 5;
+    napi_value argv[5];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    View<int32_t> tv;
+    View<double> tc;
+    if (!box || !view(env, argv[3], napi_int32_array, &tv) || !view(env, argv[4], napi_float64_array, &tc)) return nullptr;
+    if (tv.n != tc.n) {
+        napi_throw_range_error(env, nullptr, "addConstraint: termVars and termCoefs differ in length");
+        return nullptr;
+    }
+    if (throw_if(env, jslp_add_constraint(box->tab, truthy(env, argv[0]), num(env, argv[1]), (int)num(env, argv[2]), tv.data, tc.data, (int)tv.n)))
+        return nullptr;
+    return undefined(env);
+}
+napi_value tab_remove_constraint(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    if (!box || throw_if(env, jslp_remove_constraint(box->tab, (int)num(env, argv[0])))) return nullptr;
+    return undefined(env);
+}
+napi_value tab_add_variable(napi_env env, napi_callback_info info) {      // (varIndex, costEntry, optSlot, isInteger, isUnrestricted)
+    size_t argc = 5;
+    napi_value argv[5];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    if (!box || throw_if(env, jslp_add_variable(box->tab, (int)num(env, argv[0]), num(env, argv[1]), (int)num(env, argv[2], -1),
+                                                truthy(env, argv[3]), truthy(env, argv[4]))))
+        return nullptr;
+    return undefined(env);
+}
+napi_value tab_remove_variable(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    TabBox *box = unwrap(env, info, &argc, argv);
+    if (!box || throw_if(env, jslp_remove_variable(box->tab, (int)num(env, argv[0])))) return nullptr;
+    return undefined(env);
+}
+napi_value tab_info(napi_env env, napi_callback_info info) {  // {width, height, nVars, lastElementIndex}
+    size_t argc = 0;
+    TabBox *box = unwrap(env, info, &argc, nullptr);
+    int32_t v[6];
+    if (!box || throw_if(env, jslp_tab_info(box->tab, v))) return nullptr;
+    napi_value o;
+    napi_create_object(env, &o);
+    set_num(env, o, "width", v[0]);
+    set_num(env, o, "height", v[1]);
+    set_num(env, o, "nVars", v[2]);
+    set_num(env, o, "lastElementIndex", v[3]);
+    return o;
+}
+
 napi_value tab_destroy(napi_env env, napi_callback_info info) {
     napi_value self;
     size_t argc = 0;
@@ -539,6 +633,16 @@ napi_value init(napi_env env, napi_value exports) {
         {"pivotLog", nullptr, tab_pivot_log, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"createComm", nullptr, tab_create_comm, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"branchAndCut", nullptr, tab_branch_and_cut, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"putInBase", nullptr, tab_put_in_base, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"takeOutOfBase", nullptr, tab_take_out_of_base, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"updateRhs", nullptr, tab_update_rhs, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"updateCoefficient", nullptr, tab_update_coefficient, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"updateCost", nullptr, tab_update_cost, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"addConstraint", nullptr, tab_add_constraint, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"removeConstraint", nullptr, tab_remove_constraint, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"addVariable", nullptr, tab_add_variable, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"removeVariable", nullptr, tab_remove_variable, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"info", nullptr, tab_info, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"destroy", nullptr, tab_destroy, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"uniqueId", nullptr, tab_unique_id, nullptr, nullptr, nullptr, napi_static, nullptr},
     };

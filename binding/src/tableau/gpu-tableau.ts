@@ -18,6 +18,7 @@
 import Tableau from "./tableau";
 import { SlackVariable } from "../expressions";
 import type Model from "../model";
+import type { Constraint, Variable } from "../expressions";
 import type { BranchCut, VariableValue } from "./types";
 import type { BranchAndCutService } from "./branch-and-cut";
 
@@ -49,6 +50,15 @@ interface GpuTab {
     isIntegral(): boolean; mostFractional(): VariableValue;
     download(what: { matrix?: boolean; rhs?: boolean; cost?: boolean; maps?: boolean; opt?: number }): Downloaded;
     pivotLog(): Int32Array; createComm(id: Uint8Array, rank: number, nRanks: number): void;
+    putInBase(varIndex: number): number; takeOutOfBase(varIndex: number): number;
+    updateRhs(constraintIndex: number, difference: number): void;
+    updateCoefficient(constraintIndex: number, varIndex: number, difference: number): void;
+    updateCost(varIndex: number, optSlot: number, difference: number): void;
+    addConstraint(isUpperBound: boolean, rhs: number, slackIndex: number, termVars: Int32Array, termCoefs: Float64Array): void;
+    removeConstraint(slackIndex: number): void;
+    addVariable(varIndex: number, costEntry: number, optSlot: number, isInteger: boolean, isUnrestricted: boolean): void;
+    removeVariable(varIndex: number): void;
+    info(): { width: number; height: number; nVars: number; lastElementIndex: number };
     branchAndCut(opts: Record<string, unknown>): BnbResult; destroy(): void;
 }
 interface GpuAddon {
@@ -169,6 +179,61 @@ export default class GpuTableau extends Tableau {
                 (model.solutions ??= []).push(store as never);
             }
         }
+    }
+
+    // ---- dynamic-modification.ts:16-55,78-316: edits go to the device tableau, no rebuild / re-upload
+    private optSlot(priority: number): number {
+        if (priority === 0) return -1;
+        const k = this.optionalObjectives.findIndex((o) => o.priority === priority);
+        if (k < 0) throw new Error("GpuTableau: an optional objective with a new priority needs setModel() again");
+        return k;
+    }
+    private resync(): void {
+        const i = this.tab().info();
+        this.width = i.width; this.height = i.height; this.nVars = i.nVars; this.lastElementIndex = i.lastElementIndex;
+        this.syncFromDevice();
+    }
+    getNewElementIndex(): number {
+        if (this.availableIndexes.length > 0) return this.availableIndexes.pop() as number;
+        this.lastElementIndex = this.tab().info().lastElementIndex;
+        return this.lastElementIndex++;
+    }
+    putInBase(varIndex: number): number { const r = this.tab().putInBase(varIndex); this.syncFromDevice(); return r; }
+    takeOutOfBase(varIndex: number): number { const c = this.tab().takeOutOfBase(varIndex); this.syncFromDevice(); return c; }
+    updateRightHandSide(constraint: Constraint, difference: number): void {
+        this.tab().updateRhs(constraint.index, difference); this.syncFromDevice();
+    }
+    updateConstraintCoefficient(constraint: Constraint, variable: Variable, difference: number): void {
+        if (constraint.index === variable.index) {
+            throw new Error("[Tableau.updateConstraintCoefficient] constraint index should not be equal to variable index !");
+        }
+        this.tab().updateCoefficient(constraint.index, variable.index, difference); this.syncFromDevice();
+    }
+    updateCost(variable: Variable, difference: number): void {
+        this.tab().updateCost(variable.index, this.optSlot(variable.priority), difference); this.syncFromDevice();
+    }
+    addConstraint(constraint: Constraint): void {
+        this.tab().addConstraint(constraint.isUpperBound, constraint.rhs, constraint.index,
+                                 Int32Array.from(constraint.terms.map((t) => t.variable.index)),
+                                 Float64Array.from(constraint.terms.map((t) => t.coefficient)));
+        this.resync();
+    }
+    removeConstraint(constraint: Constraint): void {
+        this.tab().removeConstraint(constraint.index);
+        this.availableIndexes.push(constraint.index);       // dynamic-modification.ts:246
+        constraint.slack.index = -1;                        // :248
+        this.resync();
+    }
+    addVariable(variable: Variable): void {
+        const cost = this.model!.isMinimization === true ? -variable.cost : variable.cost;   // :258
+        this.tab().addVariable(variable.index, cost, this.optSlot(variable.priority), variable.isInteger === true,
+                               this.unrestrictedVars[variable.index] === true);
+        this.resync();
+    }
+    removeVariable(variable: Variable): void {
+        this.tab().removeVariable(variable.index);
+        this.availableIndexes.push(variable.index);         // :313
+        this.resync();
     }
 
     /** Whole matrix on the host (MIR cuts, dynamic-modification API, debugging): one D2H copy of H*W doubles. */
