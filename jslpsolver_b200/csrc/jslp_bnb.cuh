@@ -587,7 +587,11 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
         std::vector<Branch *> todo;
         // U = incumbent bound of the round (see eval_nodes_slots): committed incumbent and cached integral results
         double U = bestEvaluation;
-        while (!branches.empty() && (int)todo.size() < width) {
+        // the scan is bounded: once the un-evaluated nodes thin out it would otherwise walk the whole heap every
+        // round (entries with a cached result are popped and pushed back); candidates that far down the pop order
+        // are not popped before the next round anyway
+        const size_t scan_cap = (size_t)width * 4 + 32;
+        while (!branches.empty() && (int)todo.size() < width && taken.size() < scan_cap) {
             Frontier::Entry e = branches.pop_entry();
             // nodes that will be skipped at pop (branch-and-cut.ts:90-92) stay in the heap -- their pop
             // still consumes a loop iteration of the reference -- but are never evaluated
