@@ -89,6 +89,8 @@ enum {
                                   time (the reference's literal applyCuts sequence), n = at most n slots */
     JSLP_OPT_SLOT_STEPS = 11,  /* pivots per slot between host polls of the slot batch (default 32)   */
     JSLP_OPT_SLOT_VARIANT = 12, /* kernel instantiation used by the slot batch (JSLP_OPT_STEP_VARIANT values) */
+    JSLP_OPT_NODE_LOG_CAP = 14, /* pivot-log entries per node LP of the shared-memory node kernel (default 512); a node
+                                   that needs more is re-evaluated on the HBM path (tests lower it to hit that path) */
     JSLP_OPT_USE_MIR_CUTS = 13  /* model.useMIRCuts (model.ts:69,313): applyCuts / branchAndCut run the MIR loop of
                                    branch-and-cut.ts:38-51 after every node's simplex()                          */
 };

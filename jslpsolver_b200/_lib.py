@@ -11,7 +11,7 @@ _LIB = None
 
 OPT_ENGINE, OPT_BATCH, OPT_PIVOT_LOG_CAP = 1, 2, 3
 OPT_STEP_VARIANT, OPT_GRID_PER_SM, OPT_LOOKAHEAD, OPT_TIMELINE, OPT_PDL, OPT_PINGPONG = 4, 5, 6, 7, 8, 9
-OPT_NODE_SLOTS, OPT_SLOT_STEPS, OPT_SLOT_VARIANT, OPT_USE_MIR_CUTS = 10, 11, 12, 13
+OPT_NODE_SLOTS, OPT_SLOT_STEPS, OPT_SLOT_VARIANT, OPT_USE_MIR_CUTS, OPT_NODE_LOG_CAP = 10, 11, 12, 13, 14
 ENGINE_AUTO, ENGINE_TWO_KERNEL, ENGINE_FUSED, ENGINE_PERSISTENT, ENGINE_RESIDENT = 0, 1, 2, 3, 4
 
 

@@ -161,6 +161,7 @@ struct jslp_tab {
     std::vector<int> h_intpos;  // host copy of TabDev.intpos (computeFractionalVolume runs on the host)
     int *d_count = nullptr, *h_count = nullptr;
     int node_slots = -1;    // JSLP_OPT_NODE_SLOTS: -1 = auto, 0 = off (one node at a time), n = at most n slots
+    int node_log_cap = 512; // pivot-log entries per node of the shared-memory node kernel (overflow -> HBM path)
     int slot_steps = 32;    // pivots per slot per host poll
     int slot_variant = 12;  // kernel instantiation of the slot batch: flat streaming, 3 CTAs per SM (more row CTAs per slot)
     long long node_kernel_ns = 0;  // sum over rounds of the slowest node CTA (reporting)
@@ -431,6 +432,10 @@ extern "C" int jslp_tab_set_option(jslp_tab *t, int key, double value) {
         case JSLP_OPT_NODE_SLOTS:
             if (value < -1 || value > 64) return fail(JSLP_E_INVALID, "node slots must be -1..64");
             t->node_slots = (int)value;
+            return JSLP_OK;
+        case JSLP_OPT_NODE_LOG_CAP:
+            if (value < 2 || value > 65536) return fail(JSLP_E_INVALID, "node log cap must be 2..65536");
+            t->node_log_cap = (int)value;
             return JSLP_OK;
         case JSLP_OPT_USE_MIR_CUTS:
             t->use_mir = value != 0;

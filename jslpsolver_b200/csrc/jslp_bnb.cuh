@@ -368,7 +368,7 @@ static int eval_nodes_resident(jslp_tab *t, jslp_bnb::Branch *const *nodes, int 
     const int Hcap = t->saved.H + maxc;
     int Ws = 0;
     const size_t smem = node_smem_bytes(Hcap, t->W, &Ws);
-    const int log_cap = 512;
+    const int log_cap = t->node_log_cap;
     int rc = rb.ensure(n, totc, log_cap);
     if (rc) return rc;
     int off = 0;

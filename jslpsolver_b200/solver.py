@@ -16,6 +16,7 @@ class Solver:
         self.max_spec_batch = 0    # branch-and-cut speculation width (0 = library default)
         self.node_slots = None     # HBM-resident node batch width (None = auto, 0 = one node at a time)
         self.slot_steps = None
+        self.options: dict = {}    # JSLP_OPT_* -> value for every tableau this solver creates (tuning / test aids)
 
     def Solve(self, model: Any, precision: Optional[float] = None, full: bool = False, validate: bool = False):
         if validate:
@@ -42,6 +43,7 @@ class Solver:
         instance.tableau.max_spec_batch = self.max_spec_batch
         instance.tableau.node_slots = self.node_slots
         instance.tableau.slot_steps = self.slot_steps
+        instance.tableau.options.update(self.options)
         solution = instance.solve()
         self.lastSolvedModel = instance
         solution.solutionSet = solution.generateSolutionSet()

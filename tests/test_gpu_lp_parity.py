@@ -248,7 +248,10 @@ def test_row_capacity_growth():
 # (engine, speculation width[, node slots, pivots per slot per poll]): "hbm_spec4" runs its rounds in HBM node
 # slots (K3, jslp_slots.cuh), the two "slots" modes force odd slot counts / tiny poll windows
 BNB_MODES = {"hbm_seq": (2, 1), "auto_seq": (0, 1), "auto_spec8": (0, 8), "auto_spec32": (0, 32), "hbm_spec4": (2, 4),
-             "hbm_slots3_steps5": (2, 16, 3, 5), "hbm_noslots_spec4": (2, 4, 0, 32)}
+             "hbm_slots3_steps5": (2, 16, 3, 5), "hbm_noslots_spec4": (2, 4, 0, 32),
+             # shared-memory node kernel with a 3-entry pivot log: every node that needs more overflows and is
+             # re-evaluated on the HBM path (the boundary of jslp_bnb.cuh's log_cap / max_pivots handling)
+             "auto_spec8_logcap3": (0, 8, None, None, {14: 3})}
 
 
 @pytest.mark.parametrize("mode", list(BNB_MODES))
@@ -259,7 +262,7 @@ def test_mip_fixture_node_sequence(fx, mode):
     whatever the speculation width or evaluation back-end."""
     import jslpsolver_b200 as J
     from oracle import ref_model
-    if fx["file"] == "Monster_II.json" and mode not in ("hbm_seq", "auto_spec8", "hbm_slots3_steps5"):
+    if fx["file"] == "Monster_II.json" and mode not in ("hbm_seq", "auto_spec8", "hbm_slots3_steps5", "auto_spec8_logcap3"):
         pytest.skip("large MIP: covered by two modes")
     if fx["file"] == "Vendor Selection.json" and mode != "auto_spec32":
         pytest.skip("long MIP: covered by one mode")
@@ -270,7 +273,9 @@ def test_mip_fixture_node_sequence(fx, mode):
     s = J.Solver()
     s.engine, s.max_spec_batch = BNB_MODES[mode][:2]
     if len(BNB_MODES[mode]) > 2:
-        s.node_slots, s.slot_steps = BNB_MODES[mode][2:]
+        s.node_slots, s.slot_steps = BNB_MODES[mode][2:4]
+    if len(BNB_MODES[mode]) > 4:
+        s.options = dict(BNB_MODES[mode][4])
     gsol = s.Solve(jm, full=True)
     gt = gsol._tableau
     onl, gnl = osol.tableau.node_log(), gt.node_log()
@@ -567,3 +572,25 @@ def test_enhanced_service_matches_oracle(fx, opts):
     assert gt.branchAndCutIterations == osol.state.bncIterations
     assert same_bits(gt.matrix2d(), osol.tableau.matrix())
     assert s._simplified(gsol) == ref_model.simplify(osol)
+
+
+# ------------------------------------------------------------------ shape limits
+def test_tall_tableau_takes_the_in_place_step_and_still_matches():
+    """More than 32 rows per row CTA (H > ~9.4 k): the ping-pong step does not apply, the in-place step runs."""
+    from jslpsolver_b200 import problems
+    it = problems.dense_packing_lp_tableau(40, 10000, seed=8)
+    o = oracle_lp(it)
+    o.simplex()
+    g = gpu_lp(it, 2)
+    g.simplex()
+    assert_lp_parity(g, o, "tall 10001 x 41")
+
+
+def test_too_wide_tableau_fails_loudly():
+    """The pivot row is staged whole in shared memory: beyond 25 600 columns jslp_tab_create reports JSLP_E_CAPACITY."""
+    from jslpsolver_b200 import JslpError
+    from jslpsolver_b200.tableau import GpuTableau
+    M = np.zeros((3, 26001))
+    g = GpuTableau(1e-8)
+    with pytest.raises(JslpError, match="width exceeds"):
+        g.upload(M, np.array([-1, 0, 1], dtype=np.int32), np.concatenate([[-1], 2 + np.arange(26000)]).astype(np.int32))
