@@ -442,8 +442,9 @@ napi_value tab_branch_and_cut(napi_env env, napi_callback_info info) {
         size_t len = 0;
         if (!is_nullish(env, prop(env, o, "nodeSelection"))) napi_get_value_string_utf8(env, prop(env, o, "nodeSelection"), ns, sizeof(ns), &len);
         if (!is_nullish(env, prop(env, o, "branching"))) napi_get_value_string_utf8(env, prop(env, o, "branching"), br, sizeof(br), &len);
-        if (ns[0] || br[0] || truthy(env, prop(env, o, "enhanced"))) {
-            opts.service = 1;
+        const bool incremental = truthy(env, prop(env, o, "useIncremental"));
+        if (ns[0] || br[0] || incremental || truthy(env, prop(env, o, "enhanced"))) {
+            opts.service = incremental ? 2 : 1;  // main.ts:62-83: useIncremental wins over nodeSelection / branching
             opts.node_selection = !std::strcmp(ns, "best-first") ? 1 : !std::strcmp(ns, "depth-first") ? 2 : 3;
             opts.branching = !std::strcmp(br, "most-fractional") ? 1 : !std::strcmp(br, "strong") ? 3 : 2;
             opts.strong_candidates = (int32_t)num(env, prop(env, o, "strongBranchingCandidates"));

@@ -27,6 +27,19 @@ export function createGpuEnhancedBranchAndCutService(options: {
     };
 }
 
+/** The incremental service (incremental-branch-and-cut.ts, options.useIncremental) on the device tableau: the enhanced
+ *  loop with parent checkpoints kept in HBM. */
+export function createGpuIncrementalBranchAndCutService(options: {
+    nodeSelection?: "best-first" | "depth-first" | "hybrid";
+    branching?: "most-fractional" | "pseudocost" | "strong";
+} = {}): BranchAndCutService {
+    const strategy = { useIncremental: true, nodeSelection: options.nodeSelection ?? "hybrid", branching: options.branching ?? "pseudocost" };
+    return {
+        applyCuts(tableau: Tableau, cuts: BranchCut[]): void { (tableau as GpuTableau).applyCuts(cuts); },
+        branchAndCut(tableau: Tableau): void { (tableau as GpuTableau).runBranchAndCut(strategy); },
+    };
+}
+
 export function createGpuBranchAndCutService(): BranchAndCutService {
     const host = createBranchAndCutService();
     return {

@@ -227,7 +227,8 @@ typedef struct {
     double timeout_ms;      /* model.timeout (branch-and-cut.ts:61-63,76), wall clock, 0 = none              */
     /* Which BranchAndCutService main.ts:62-83 would have injected: 0 = createBranchAndCutService (default;
      * speculative frontier, node slots, multi-GPU), 1 = createEnhancedBranchAndCutService (options.nodeSelection /
-     * options.branching; pseudocosts make it sequential: one node LP at a time, one GPU).                     */
+     * options.branching; pseudocosts make it sequential: one node LP at a time, one GPU), 2 =
+     * createIncrementalBranchAndCutService (options.useIncremental: the enhanced loop with parent checkpoints).  */
     int32_t service;
     int32_t node_selection;    /* enhanced: 1 = "best-first", 2 = "depth-first", 3 = "hybrid" (0 = its default, hybrid) */
     int32_t branching;         /* enhanced: 1 = "most-fractional", 2 = "pseudocost", 3 = "strong" (0 = pseudocost)      */

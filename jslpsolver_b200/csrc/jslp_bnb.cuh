@@ -460,7 +460,7 @@ extern "C" int jslp_branch_and_cut(jslp_tab *t, const jslp_bnb_opts *opts, jslp_
     const int n_ranks = std::max(1, opts->n_ranks), rank = opts->rank;
     if (n_ranks > 1 && !opts->all_gather && !opts->comm) return fail(JSLP_E_INVALID, "n_ranks > 1 needs a communicator or an all_gather hook");
     if (n_ranks > 1 && t->nOpt > 7) return fail(JSLP_E_UNSUPPORTED, "more than 7 optional objectives across ranks");
-    if (opts->service == 1) return bnb_enhanced(t, opts, out, best_cuts, best_cuts_cap);  // sequential by construction
+    if (opts->service == 1 || opts->service == 2) return bnb_enhanced(t, opts, out, best_cuts, best_cuts_cap);  // sequential by construction
     if (opts->service != 0) return fail(JSLP_E_UNSUPPORTED, "unknown branch-and-cut service");
     jslp_ctx *ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));

@@ -7,6 +7,11 @@
 // The pseudocost table is updated from every evaluated node IN ORDER and decides later branching variables, so this
 // service is sequential by construction: one node LP at a time on the single-tableau HBM path (restore, cut rows,
 // fused pivot steps), the policy on the host.  Same kernels as the default service, different frontier.
+//
+// The same loop also replaces createIncrementalBranchAndCutService (incremental-branch-and-cut.ts:128-499,
+// options.useIncremental, "experimental" in the reference): depth-first children restore a CHECKPOINT of their parent's
+// solved tableau (device-to-device copy, at most maxCheckpoints = 50 per call) and add only their one new cut instead
+// of restoring the root and re-adding every cut; pseudocosts are fed by `newCut`; "strong" means pseudocost.
 #pragma once
 
 #include <chrono>
@@ -28,6 +33,50 @@ static double pc_score(const PseudoCost &d, double fraction) {
     auto max6 = [](double x) { return x > 1e-6 ? x : (x != x ? x : 1e-6); };  // Math.max(x, 1e-6)
     return max6(upEstimate) * max6(downEstimate);
 }
+
+// StateCheckpoint (incremental-branch-and-cut.ts:28-107): the solved parent tableau, kept on the device
+struct DevCheckpoint {
+    double *M = nullptr;
+    int *vrow = nullptr, *vcol = nullptr;
+    int H = 0, W = 0, stride = 0, nVars = 0, lastElementIndex = 0, feasible = 1;
+    double evaluation = 0;
+    ~DevCheckpoint() { cudaFree(M); cudaFree(vrow); cudaFree(vcol); }
+};
+static int checkpoint_create(jslp_tab *t, std::shared_ptr<DevCheckpoint> *out) {
+    std::shared_ptr<DevCheckpoint> c(new DevCheckpoint());
+    cudaStream_t s = t->ctx->stream;
+    c->H = t->H; c->W = t->W; c->stride = t->stride; c->nVars = t->nVars; c->lastElementIndex = t->lastElementIndex;
+    c->feasible = t->feasible; c->evaluation = t->evaluation;
+    CK(cudaMalloc(&c->M, sizeof(double) * (size_t)t->H * t->stride));
+    CK(cudaMalloc(&c->vrow, sizeof(int) * (size_t)t->H));
+    CK(cudaMalloc(&c->vcol, sizeof(int) * (size_t)t->W));
+    CK(cudaMemcpyAsync(c->M, t->hd.M, sizeof(double) * (size_t)t->H * t->stride, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(c->vrow, t->hd.vrow, sizeof(int) * (size_t)t->H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(c->vcol, t->hd.vcol, sizeof(int) * (size_t)t->W, cudaMemcpyDeviceToDevice, s));
+    *out = c;
+    return JSLP_OK;
+}
+static int checkpoint_restore(jslp_tab *t, const DevCheckpoint &c) {
+    if (c.stride != t->stride || c.W != t->W) return fail(JSLP_E_INVALID, "checkpoint of another layout");
+    int rc = grow_rows(t, c.H);
+    if (rc) return rc;
+    cudaStream_t s = t->ctx->stream;
+    CK(cudaMemcpyAsync(t->hd.M, c.M, sizeof(double) * (size_t)c.H * t->stride, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vrow, c.vrow, sizeof(int) * (size_t)c.H, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(t->hd.vcol, c.vcol, sizeof(int) * (size_t)c.W, cudaMemcpyDeviceToDevice, s));
+    const int grid_before = step_grid(t);
+    t->H = c.H; t->nVars = c.nVars; t->lastElementIndex = c.lastElementIndex;
+    t->evaluation = c.evaluation; t->feasible = c.feasible;
+    rc = push_desc(t);
+    if (rc) return rc;
+    if (step_grid(t) != grid_before) drop_graphs(t);
+    return JSLP_OK;
+}
+struct IncBranchInfo {  // IncrementalBranch (incremental-branch-and-cut.ts:49-53), keyed by the Branch it extends
+    std::shared_ptr<DevCheckpoint> parent;
+    jslp_cut newCut{0, -1, 0.0};
+    bool hasNewCut = false;
+};
 
 struct FracCand {
     int index;
@@ -79,6 +128,8 @@ static int enh_select_variable(jslp_tab *t, std::unordered_map<int, PseudoCost> 
     return best.index;
 }
 
+static int enh_mir_rounds(jslp_tab *t, int check_cycles, int *pivots);
+
 // applyCuts of the enhanced service (enhanced-branch-and-cut.ts:197-221)
 static int enh_apply_cuts(jslp_tab *t, const std::vector<jslp_cut> &cuts, int check_cycles, int *pivots) {
     jslp_lp_status st;
@@ -89,25 +140,45 @@ static int enh_apply_cuts(jslp_tab *t, const std::vector<jslp_cut> &cuts, int ch
     rc = run_lp(t, 0, check_cycles, &st, false);
     if (rc) return rc;
     *pivots = st.phase1_pivots + st.phase2_pivots;
-    if (t->use_mir && t->feasible) {
-        bool improved = true;
-        int mirIterations = 0;
-        while (improved && mirIterations < 3) {
-            double before = 0, after = 0;
-            if ((rc = jslp_fractional_volume(t, 1, &before))) return rc;
-            if ((rc = mir_cuts(t, -1, 0, nullptr))) return rc;
-            if ((rc = run_lp(t, 0, check_cycles, &st, false))) return rc;
-            *pivots += st.phase1_pivots + st.phase2_pivots;
-            if ((rc = jslp_fractional_volume(t, 1, &after))) return rc;
-            mirIterations++;
-            if (after >= 0.9 * before) improved = false;
-        }
+    return enh_mir_rounds(t, check_cycles, pivots);
+}
+
+// the MIR rounds shared by applyCuts / applyIncrementalCuts (enhanced :204-220, incremental :263-280)
+static int enh_mir_rounds(jslp_tab *t, int check_cycles, int *pivots) {
+    if (!(t->use_mir && t->feasible)) return JSLP_OK;
+    jslp_lp_status st;
+    bool improved = true;
+    int mirIterations = 0, rc;
+    while (improved && mirIterations < 3) {
+        double before = 0, after = 0;
+        if ((rc = jslp_fractional_volume(t, 1, &before))) return rc;
+        if ((rc = mir_cuts(t, -1, 0, nullptr))) return rc;
+        if ((rc = run_lp(t, 0, check_cycles, &st, false))) return rc;
+        *pivots += st.phase1_pivots + st.phase2_pivots;
+        if ((rc = jslp_fractional_volume(t, 1, &after))) return rc;
+        mirIterations++;
+        if (after >= 0.9 * before) improved = false;
     }
     return JSLP_OK;
 }
 
+// applyIncrementalCuts fast path (incremental-branch-and-cut.ts:253-258): parent checkpoint + the one new cut
+static int inc_apply_cuts(jslp_tab *t, const DevCheckpoint &parent, const jslp_cut &newCut, int check_cycles, int *pivots) {
+    jslp_lp_status st;
+    int rc = checkpoint_restore(t, parent);
+    if (rc) return rc;
+    if ((rc = jslp_add_cuts(t, &newCut, 1))) return rc;
+    if ((rc = run_lp(t, 0, check_cycles, &st, false))) return rc;
+    *pivots = st.phase1_pivots + st.phase2_pivots;
+    return enh_mir_rounds(t, check_cycles, pivots);
+}
+
 static int bnb_enhanced(jslp_tab *t, const jslp_bnb_opts *opts, jslp_bnb_status *out, jslp_cut *best_cuts, int best_cuts_cap) {
     using namespace jslp_bnb;
+    const bool incremental = opts->service == 2;
+    const int maxCheckpoints = 50;  // incremental-branch-and-cut.ts:135
+    int checkpointCount = 0;
+    std::unordered_map<const Branch *, IncBranchInfo> inc;
     jslp_ctx *ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
@@ -118,7 +189,8 @@ static int bnb_enhanced(jslp_tab *t, const jslp_bnb_opts *opts, jslp_bnb_status 
                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count() >= opts->timeout_ms;
     };
     const int nodeSelection = opts->node_selection > 0 ? opts->node_selection : 3;  // default "hybrid"
-    const int branching = opts->branching > 0 ? opts->branching : 2;               // default "pseudocost"
+    int branching = opts->branching > 0 ? opts->branching : 2;                     // default "pseudocost"
+    if (incremental && branching == 3) branching = 2;                              // incremental :203-219: no strong variant
     const int strongCandidates = opts->strong_candidates > 0 ? opts->strong_candidates : 5;
     const int check_cycles = opts->check_cycles;
     const double tolerance = opts->tolerance;
@@ -150,10 +222,16 @@ static int bnb_enhanced(jslp_tab *t, const jslp_bnb_opts *opts, jslp_bnb_status 
         if (useDepthFirst && !stack.empty()) { active = std::move(stack.back()); stack.pop_back(); }
         else if (!branches.empty()) active = std::move(branches.pop_entry().b);
         else break;
+        IncBranchInfo info;
+        if (incremental) {  // taken out of the table whatever happens next: the Branch's address may be reused
+            auto it = inc.find(active.get());
+            if (it != inc.end()) { info = it->second; inc.erase(it); }
+        }
         if (active->relaxedEvaluation > bestEvaluation) continue;
         const double parentEval = t->evaluation;
         int node_pivots = 0;
-        int rc = enh_apply_cuts(t, active->cuts, check_cycles, &node_pivots);
+        int rc = (incremental && info.parent && info.hasNewCut) ? inc_apply_cuts(t, *info.parent, info.newCut, check_cycles, &node_pivots)
+                                                                : enh_apply_cuts(t, active->cuts, check_cycles, &node_pivots);
         if (rc) return rc;
         iterations++; nodes++; pivots += node_pivots;
         NodeLogEntry nl;
@@ -162,8 +240,8 @@ static int bnb_enhanced(jslp_tab *t, const jslp_bnb_opts *opts, jslp_bnb_status 
         if (!t->feasible) { t->node_log.push_back(nl); continue; }
         const double evaluation = t->evaluation;
         if (evaluation > bestEvaluation) { t->node_log.push_back(nl); continue; }
-        if (!active->cuts.empty() && parentEval != 0) {  // enhanced-branch-and-cut.ts:281-294
-            const jslp_cut &lastCut = active->cuts.back();
+        if ((incremental ? info.hasNewCut : !active->cuts.empty()) && parentEval != 0) {  // enhanced :281-294, incremental :353-362
+            const jslp_cut lastCut = incremental ? info.newCut : active->cuts.back();
             const double improvement = std::fabs(evaluation - parentEval);
             const double fraction = 0.5;
             PseudoCost &d = pseudoCosts[lastCut.var_index];
@@ -238,6 +316,16 @@ static int bnb_enhanced(jslp_tab *t, const jslp_bnb_opts *opts, jslp_bnb_status 
             }
             high->cuts.push_back(jslp_cut{0, varIndex, std::ceil(varValue)});
             low->cuts.push_back(jslp_cut{1, varIndex, std::floor(varValue)});
+            if (incremental && useDepthFirst) {  // incremental :435-438,476-483: children carry the parent checkpoint + their cut
+                std::shared_ptr<DevCheckpoint> cp;
+                if (checkpointCount < maxCheckpoints) {
+                    rc = checkpoint_create(t, &cp);
+                    if (rc) return rc;
+                    checkpointCount++;
+                }
+                inc[low.get()] = IncBranchInfo{cp, low->cuts.back(), true};
+                inc[high.get()] = IncBranchInfo{cp, high->cuts.back(), true};
+            }
             if (useDepthFirst) { stack.push_back(std::move(low)); stack.push_back(std::move(high)); }  // 'up' branch first
             else { branches.push(std::move(high)); branches.push(std::move(low)); }
         }

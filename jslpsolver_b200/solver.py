@@ -30,13 +30,11 @@ class Solver:
             if model.get("external"):
                 raise NotImplementedError("external solvers (src/external) are out of scope")
             options = model.get("options") or {}
-            if options.get("useIncremental") is True:
-                raise NotImplementedError(
-                    "the incremental branch-and-cut service (experimental, opt-in; it re-solves from parent checkpoints, "
-                    "so its numerics differ from every other path) is outside the GPU hot-path scope (SURVEY.md 8f.3)")
             instance = Model(precision).loadJson(model)
-            if options.get("nodeSelection") or options.get("branching"):  # selectBranchAndCutService, main.ts:62-83
-                instance.branchAndCutOptions = {"nodeSelection": options.get("nodeSelection"), "branching": options.get("branching")}
+            # selectBranchAndCutService (main.ts:62-83): incremental if explicitly asked, else enhanced if a strategy is named
+            if options.get("useIncremental") is True or options.get("nodeSelection") or options.get("branching"):
+                instance.branchAndCutOptions = {"nodeSelection": options.get("nodeSelection"), "branching": options.get("branching"),
+                                                "useIncremental": options.get("useIncremental") is True}
         else:
             instance = model
         instance.tableau.engine = self.engine

@@ -426,7 +426,7 @@ class GpuTableau:
         opts.shard_policy = int(self.shard_policy)
         sel = getattr(m, "branchAndCutOptions", None)  # main.ts:62-83: options.nodeSelection / options.branching
         if sel:
-            opts.service = 1
+            opts.service = 2 if sel.get("useIncremental") else 1
             opts.node_selection = {"best-first": 1, "depth-first": 2, "hybrid": 3}[sel.get("nodeSelection") or "hybrid"]
             opts.branching = {"most-fractional": 1, "pseudocost": 2, "strong": 3}[sel.get("branching") or "pseudocost"]
         opts.max_nodes = int(getattr(m, "max_nodes", 0) or 0)

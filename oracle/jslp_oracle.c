@@ -18,6 +18,7 @@
  *   cutting-strategies.ts:74-212 addLowerBoundMIRCut / addUpperBoundMIRCut / applyMIRCuts -> orc_add_mir_cut / orc_apply_mir_cuts
  *   mip-utils.ts:67-98  computeFractionalVolume -> orc_fractional_volume
  *   enhanced-branch-and-cut.ts:54-437  createEnhancedBranchAndCutService -> orc_enhanced_branch_and_cut
+ *   incremental-branch-and-cut.ts:28-499 createIncrementalBranchAndCutService -> orc_enhanced_branch_and_cut(incremental = 1)
  *   dynamic-modification.ts:16-316 putInBase / takeOutOfBase / updateRightHandSide / updateConstraintCoefficient /
  *                       updateCost / addConstraint / removeConstraint / addVariable / removeVariable -> orc_dm_*
  *   mip-utils.ts:43-61,100-126  isIntegral / getMostFractionalVar
@@ -48,6 +49,10 @@ typedef struct {
     double relaxedEvaluation;
     orc_cut *cuts;
     int nCuts;
+    /* incremental service only (incremental-branch-and-cut.ts:49-53) */
+    void *parentCheckpoint;
+    orc_cut newCut;
+    int hasNewCut;
 } orc_branch;
 
 typedef struct {
@@ -944,10 +949,12 @@ static orc_branch *heap_pop(minheap *hp) {
 static orc_branch *make_branch(double ev, int nCuts) {
     orc_branch *b = (orc_branch *)malloc(sizeof(orc_branch));
     b->relaxedEvaluation = ev; b->nCuts = 0;
+    b->parentCheckpoint = 0; b->hasNewCut = 0;
     b->cuts = (orc_cut *)malloc(sizeof(orc_cut) * (nCuts > 0 ? nCuts : 1));
     return b;
 }
-static void free_branch(orc_branch *b) { if (b) { free(b->cuts); free(b); } }
+static void checkpoint_release_v(void *c);
+static void free_branch(orc_branch *b) { if (b) { if (b->parentCheckpoint) checkpoint_release_v(b->parentCheckpoint); free(b->cuts); free(b); } }
 
 /* branch-and-cut.ts:33-52 */
 static void apply_cuts(orc_tab *t, const orc_cut *cuts, int n) {
@@ -1074,6 +1081,51 @@ done:
     free(bestOpt);
 }
 
+/* ---- incremental-branch-and-cut.ts:28-107: StateCheckpoint / createCheckpoint / restoreCheckpoint ---- */
+typedef struct {
+    int W, H, nVars, lastElementIndex, feasible, refs, mapLen;
+    double evaluation;
+    double *M;
+    int *vrow, *vcol, *rowOf, *colOf;
+} orc_checkpoint;
+
+static orc_checkpoint *checkpoint_create(const orc_tab *t) {
+    orc_checkpoint *c = (orc_checkpoint *)calloc(1, sizeof(orc_checkpoint));
+    c->W = t->W; c->H = t->H; c->nVars = t->nVars; c->lastElementIndex = t->lastElementIndex;
+    c->feasible = t->feasible; c->evaluation = t->evaluation; c->refs = 0;
+    c->M = (double *)malloc(sizeof(double) * (size_t)t->H * t->W);
+    memcpy(c->M, t->M, sizeof(double) * (size_t)t->H * t->W);
+    c->vrow = (int *)malloc(sizeof(int) * t->H);
+    memcpy(c->vrow, t->vrow, sizeof(int) * t->H);
+    c->vcol = (int *)malloc(sizeof(int) * t->W);
+    memcpy(c->vcol, t->vcol, sizeof(int) * t->W);
+    c->mapLen = t->mapCap;
+    c->rowOf = (int *)malloc(sizeof(int) * t->mapCap);
+    c->colOf = (int *)malloc(sizeof(int) * t->mapCap);
+    memcpy(c->rowOf, t->rowOf, sizeof(int) * t->mapCap);
+    memcpy(c->colOf, t->colOf, sizeof(int) * t->mapCap);
+    return c;
+}
+static void checkpoint_release(orc_checkpoint *c) {
+    if (!c || --c->refs > 0) return;
+    free(c->M); free(c->vrow); free(c->vcol); free(c->rowOf); free(c->colOf); free(c);
+}
+/* :73-107: the index maps are restored for indices < checkpoint.nVars only; later entries keep what they hold */
+static void checkpoint_restore(orc_tab *t, const orc_checkpoint *c) {
+    ensure_rows(t, c->H);
+    memcpy(t->M, c->M, sizeof(double) * (size_t)c->H * c->W);
+    t->W = c->W; t->H = c->H; t->nVars = c->nVars;
+    memcpy(t->vrow, c->vrow, sizeof(int) * c->H);
+    memcpy(t->vcol, c->vcol, sizeof(int) * c->W);
+    ensure_maps(t, c->nVars);
+    for (int i = 0; i < c->nVars && i < c->mapLen; i++) { t->rowOf[i] = c->rowOf[i]; t->colOf[i] = c->colOf[i]; }
+    t->lastElementIndex = c->lastElementIndex;
+    t->evaluation = c->evaluation;
+    t->feasible = c->feasible;
+}
+
+static void checkpoint_release_v(void *c) { checkpoint_release((orc_checkpoint *)c); }
+
 /* ---- enhanced-branch-and-cut.ts ---- */
 typedef struct { double upSum, downSum; long upCount, downCount; } pseudo_cost;
 typedef struct { int index; double value, fraction; } frac_cand;
@@ -1165,7 +1217,16 @@ static void enh_apply_cuts(orc_tab *t, const orc_cut *cuts, int n) {
 
 /* :223-434.  nodeSelection: 1 = best-first, 2 = depth-first, 3 = hybrid; branching as above.  One service instance per
  * call (main.ts:62-83 creates a fresh one per Solve), so the pseudocosts start empty. */
+void orc_enhanced_branch_and_cut2(orc_tab *t, int nodeSelection, int branching, int strongCandidates, int incremental, int maxCheckpoints);
 void orc_enhanced_branch_and_cut(orc_tab *t, int nodeSelection, int branching, int strongCandidates) {
+    orc_enhanced_branch_and_cut2(t, nodeSelection, branching, strongCandidates, 0, 0);
+}
+/* incremental != 0: createIncrementalBranchAndCutService (incremental-branch-and-cut.ts:128-499) -- the same loop with
+ * parent checkpoints: a depth-first child restores its parent's solved tableau and adds only its new cut (at most
+ * maxCheckpoints checkpoints per call, :435-438), pseudocosts are fed by `newCut` (:353-362), "strong" means pseudocost. */
+void orc_enhanced_branch_and_cut2(orc_tab *t, int nodeSelection, int branching, int strongCandidates, int incremental, int maxCheckpoints) {
+    int checkpointCount = 0;
+    if (incremental && branching == 3) branching = 2;
     minheap hp = {0, 0, 0, 0};
     orc_branch **stack = 0;
     long sp = 0, scap = 0;
@@ -1196,7 +1257,24 @@ void orc_enhanced_branch_and_cut(orc_tab *t, int nodeSelection, int branching, i
         if (active->relaxedEvaluation > bestEvaluation) { free_branch(active); continue; }
         const double parentEval = t->evaluation;
         const long pivBefore = t->totalPivots;
-        enh_apply_cuts(t, active->cuts, active->nCuts);
+        if (incremental && active->parentCheckpoint && active->hasNewCut) {  /* applyIncrementalCuts :253-261 */
+            checkpoint_restore(t, (const orc_checkpoint *)active->parentCheckpoint);
+            orc_add_cuts(t, &active->newCut, 1);
+            orc_simplex(t);
+            if (t->useMIR && t->feasible) {
+                int improved = 1, mirIterations = 0;
+                while (improved && mirIterations < 3) {
+                    const double before = orc_fractional_volume(t, 1);
+                    orc_apply_mir_cuts(t);
+                    orc_simplex(t);
+                    const double after = orc_fractional_volume(t, 1);
+                    mirIterations++;
+                    if (after >= 0.9 * before) improved = 0;
+                }
+            }
+        } else {
+            enh_apply_cuts(t, active->cuts, active->nCuts);
+        }
         iterations++;
         double *nl = 0;
         if (t->nlog && t->nlogN < t->nlogCap) {
@@ -1208,8 +1286,8 @@ void orc_enhanced_branch_and_cut(orc_tab *t, int nodeSelection, int branching, i
         if (!t->feasible) { free_branch(active); continue; }
         const double evaluation = t->evaluation;
         if (evaluation > bestEvaluation) { free_branch(active); continue; }
-        if (active->nCuts > 0 && parentEval != 0) {  /* :281-294 */
-            const orc_cut lastCut = active->cuts[active->nCuts - 1];
+        if ((incremental ? active->hasNewCut : active->nCuts > 0) && parentEval != 0) {  /* :281-294 / incremental :353-362 */
+            const orc_cut lastCut = incremental ? active->newCut : active->cuts[active->nCuts - 1];
             const double improvement = fabs(evaluation - parentEval);
             const double fraction = 0.5;
             if (lastCut.varIndex >= 0 && lastCut.varIndex < pcN) {
@@ -1265,6 +1343,13 @@ void orc_enhanced_branch_and_cut(orc_tab *t, int nodeSelection, int branching, i
             orc_cut cl = {1, varIndex, floor(varValue)};
             high->cuts[high->nCuts++] = ch;
             low->cuts[low->nCuts++] = cl;
+            if (incremental && useDepthFirst) {  /* incremental :435-438,476-483 */
+                orc_checkpoint *cp = 0;
+                if (checkpointCount < maxCheckpoints) { cp = checkpoint_create(t); checkpointCount++; }
+                low->parentCheckpoint = cp; low->newCut = cl; low->hasNewCut = 1;
+                high->parentCheckpoint = cp; high->newCut = ch; high->hasNewCut = 1;
+                if (cp) cp->refs = 2;
+            }
             if (useDepthFirst) { STACK_PUSH(low); STACK_PUSH(high); }
             else { heap_push(&hp, high); heap_push(&hp, low); }
             free_branch(active);

@@ -96,6 +96,8 @@ def lib():
         L.orc_set_use_mir.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_enhanced_branch_and_cut.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_enhanced_branch_and_cut.restype = None
+        L.orc_enhanced_branch_and_cut2.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5
+        L.orc_enhanced_branch_and_cut2.restype = None
         for name in ("orc_dm_put_in_base", "orc_dm_take_out_of_base", "orc_dm_remove_constraint", "orc_dm_remove_variable"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int]
             getattr(L, name).restype = ctypes.c_int
@@ -647,6 +649,10 @@ class OracleTableau:
         lib().orc_enhanced_branch_and_cut(self.h, self.NODE_SELECTION[node_selection], self.BRANCHING[branching], strong_candidates)
         return self.state()
 
+    def incremental_branch_and_cut(self, node_selection="hybrid", branching="pseudocost", max_checkpoints=50):
+        lib().orc_enhanced_branch_and_cut2(self.h, self.NODE_SELECTION[node_selection], self.BRANCHING[branching], 5, 1, max_checkpoints)
+        return self.state()
+
     # ---- dynamic-modification.ts (indices instead of Constraint / Variable objects)
     def put_in_base(self, var_index):
         return lib().orc_dm_put_in_base(self.h, int(var_index))
@@ -802,8 +808,8 @@ def solve_full(jm: dict, precision=None, fast_cycles=False, pivot_log=0, node_lo
     if ints:  # tableau.ts:250-258; the service is chosen from model.options (main.ts:62-83)
         options = jm.get("options") or {}
         if options.get("useIncremental") is True:
-            raise NotImplementedError("incremental branch-and-cut service (experimental, opt-in) is not restated")
-        if js_truthy(options.get("nodeSelection")) or js_truthy(options.get("branching")):
+            st = tab.incremental_branch_and_cut(options.get("nodeSelection") or "hybrid", options.get("branching") or "pseudocost")
+        elif js_truthy(options.get("nodeSelection")) or js_truthy(options.get("branching")):
             st = tab.enhanced_branch_and_cut(options.get("nodeSelection") or "hybrid", options.get("branching") or "pseudocost")
         else:
             st = tab.branch_and_cut()

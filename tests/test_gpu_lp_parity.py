@@ -542,7 +542,10 @@ def test_model_level_edits_after_solve():
 
 # ------------------------------------------------------------------ enhanced service (enhanced-branch-and-cut.ts)
 ENHANCED = [{"nodeSelection": "hybrid"}, {"nodeSelection": "depth-first", "branching": "strong"},
-            {"nodeSelection": "best-first", "branching": "most-fractional"}, {"branching": "pseudocost", "useMIRCuts": True}]
+            {"nodeSelection": "best-first", "branching": "most-fractional"}, {"branching": "pseudocost", "useMIRCuts": True},
+            # options.useIncremental: the incremental service (parent checkpoints, incremental-branch-and-cut.ts)
+            {"useIncremental": True}, {"useIncremental": True, "nodeSelection": "depth-first", "branching": "most-fractional"},
+            {"useIncremental": True, "useMIRCuts": True}]
 
 
 @pytest.mark.parametrize("opts", ENHANCED, ids=lambda o: "-".join(str(v) for v in o.values()))

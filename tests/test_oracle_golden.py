@@ -269,7 +269,8 @@ def test_enhanced_service_known_answers():
         m = strip_timeouts(fx["model"])
         if not (m.get("ints") or m.get("binaries")) or m.get("tolerance") or (m.get("options") or {}).get("tolerance"):
             continue
-        for opts in ({"nodeSelection": "hybrid"}, {"nodeSelection": "depth-first", "branching": "strong"}, {"branching": "most-fractional"}):
+        for opts in ({"nodeSelection": "hybrid"}, {"nodeSelection": "depth-first", "branching": "strong"}, {"branching": "most-fractional"},
+                     {"useIncremental": True}, {"useIncremental": True, "nodeSelection": "depth-first"}):
             r = ref_model.Solve(dict(m, options=dict(m.get("options") or {}, **opts)), fast_cycles=True)
             bad = [b for b in compare_solutions(r, fx["expects"]) if b.startswith(("result", "feasible"))]
             assert not bad, (fx["file"], opts, bad)
