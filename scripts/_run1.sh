@@ -1,2 +1,2 @@
 set -u
-timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x -k "enhanced_service" > gpurun_out/pytest_inc.log 2>&1; echo "pytest exit $?"; tail -n 12 gpurun_out/pytest_inc.log
+timeout 600 python -m pytest tests/test_gpu_addon.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -15
