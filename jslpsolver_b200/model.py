@@ -515,12 +515,14 @@ def presolve(model: Model) -> PresolveResult:
                 continue
             amin = amax = 0.0
             for t in con.coef.values():
-                if t.variable in fixed:
+                if fixed and t.variable in fixed:
                     amin += t.coefficient * fixed[t.variable]
                     amax += t.coefficient * fixed[t.variable]
                     continue
-                lo = _get(bounds, t.variable, "lower")
-                up = _get(bounds, t.variable, "upper")
+                b = bounds.get(t.variable) if bounds else None   # one lookup per term (this loop is O(nnz) per pass)
+                lo = up = None
+                if b is not None:
+                    lo, up = b.get("lower"), b.get("upper")
                 lo = 0 if lo is None else lo
                 up = 1e10 if (up is None or up == math.inf) else up
                 if t.coefficient > 0:
@@ -549,23 +551,27 @@ def presolve(model: Model) -> PresolveResult:
                 continue
             amin = 0.0
             for t in con.coef.values():
-                if t.variable in fixed:
+                if fixed and t.variable in fixed:
                     amin += t.coefficient * fixed[t.variable]
-                elif t.coefficient > 0:
-                    lo = _get(bounds, t.variable, "lower")
+                    continue
+                b = bounds.get(t.variable) if bounds else None
+                if t.coefficient > 0:
+                    lo = None if b is None else b.get("lower")
                     amin += t.coefficient * (0 if lo is None else lo)
                 else:
-                    up = _get(bounds, t.variable, "upper")
+                    up = None if b is None else b.get("upper")
                     amin += t.coefficient * (math.inf if up is None else up)
             slack = con.rhs - amin
             if slack < 0:
                 continue
             for t in con.coef.values():
                 v = t.variable
-                if v in fixed or not v.isInteger or t.coefficient <= 0:
+                if not v.isInteger or t.coefficient <= 0 or (fixed and v in fixed):
                     continue
-                lo = _get(bounds, v, "lower")
-                up = _get(bounds, v, "upper")
+                b = bounds.get(v) if bounds else None
+                lo = up = None
+                if b is not None:
+                    lo, up = b.get("lower"), b.get("upper")
                 lo = 0 if lo is None else lo
                 up = 1 if up is None else up
                 if lo >= -0.5 and up <= 1.5 and t.coefficient * (up - lo) > slack + 1e-6:

@@ -29,10 +29,20 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def highs_objective(c, A, b, upper):
+    """Optimal objective of max c.x, A x <= b, 0 <= x <= upper by an independent solver (SciPy's HiGHS)."""
+    from scipy.optimize import linprog
+    res = linprog(-np.asarray(c, dtype=float), A_ub=np.asarray(A, dtype=float), b_ub=np.asarray(b, dtype=float),
+                  bounds=(0, upper), method="highs")
+    assert res.status == 0
+    return -res.fun
+
+
 def config3():
     from jslpsolver_b200 import problems
     from oracle import ref_model
     it = problems.dense_packing_lp_tableau(2000, 2000, seed=12345)
+    A, b, c = problems.dense_packing_lp_arrays(2000, 2000, seed=12345)
     t0 = time.time()
     o = ref_model.OracleTableau(it.matrix, it.varIndexByRow, it.varIndexByCol, fast_cycles=True, pivot_log=1 << 20)
     st = o.simplex()
@@ -42,7 +52,7 @@ def config3():
                         input_sha=np.array(sha(it.matrix)), pivot_log=o.pivot_log(), vrow=vrow, vcol=vcol,
                         rhs=M[:, 0].copy(), cost=M[0].copy(), matrix_sha=np.array(sha(M)),
                         flags=np.array([st.feasible, st.bounded, st.lastP1, st.lastP2, st.simplexIters], dtype=np.int64),
-                        evaluation=np.array([st.evaluation, M[0, 0]]))
+                        evaluation=np.array([st.evaluation, M[0, 0]]), highs_objective=np.array(highs_objective(c, A, b, None)))
     print(f"config 3: {st.lastP1}+{st.lastP2} pivots, evaluation {st.evaluation}, {time.time() - t0:.0f} s")
 
 
@@ -73,7 +83,11 @@ def config5():
     st = o.simplex()
     Mr = o.matrix()
     rvrow, rvcol = o.maps()
-    root = dict(root_input_sha=np.array(sha(M)), root_pivot_log=o.pivot_log(), root_vrow=rvrow, root_vcol=rvcol,
+    rng = np.random.default_rng(12345)  # the generator's arrays again (problems.knapsack_mip_model), for the independent solver
+    Ak = rng.integers(1, 51, size=(512, 1024))
+    ck = rng.integers(1, 51, size=1024)
+    root = dict(root_highs_objective=np.array(highs_objective(ck, Ak, np.floor(0.5 * Ak.sum(axis=1)), 1)),
+                root_input_sha=np.array(sha(M)), root_pivot_log=o.pivot_log(), root_vrow=rvrow, root_vcol=rvcol,
                 root_rhs=Mr[:, 0].copy(), root_cost=Mr[0].copy(), root_matrix_sha=np.array(sha(Mr)),
                 root_flags=np.array([st.feasible, st.bounded, st.lastP1, st.lastP2], dtype=np.int64),
                 root_evaluation=np.array([st.evaluation, Mr[0, 0]]))

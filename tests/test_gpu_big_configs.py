@@ -42,6 +42,10 @@ def check_lp(g, st, z, prefix, what):
     assert sha(M) == str(z[prefix + "matrix_sha"]), f"{what}: tableau hash differs"
     ev = z[prefix + "evaluation"]
     assert bits(st.evaluation) == bits(ev[0]) and bits(st.evaluation_raw) == bits(ev[1]), what
+    # and against a solver that shares nothing with the reference or the oracle (SciPy's HiGHS, cached by the fixture
+    # script): north_star's "objective within 1e-9 relative"
+    highs = float(z[prefix + "highs_objective"])
+    assert abs(-st.evaluation - highs) <= 1e-9 * abs(highs), (what, st.evaluation, highs)
 
 
 # (engine, look-ahead, step variant[, pdl, pingpong]) -- the benched default first

@@ -274,3 +274,66 @@ def test_enhanced_service_known_answers():
             r = ref_model.Solve(dict(m, options=dict(m.get("options") or {}, **opts)), fast_cycles=True)
             bad = [b for b in compare_solutions(r, fx["expects"]) if b.startswith(("result", "feasible"))]
             assert not bad, (fx["file"], opts, bad)
+
+
+# ------------------------------------------------------------------ independent cross-check (not the reference, not the oracle)
+def _random_model(rng, n, m, integer):
+    cons = {f"c{i}": ({"max": float(rng.integers(20, 200))} if rng.random() < 0.75 else {"min": float(rng.integers(1, 15))}) for i in range(m)}
+    vars_ = {}
+    for j in range(n):
+        v = {"obj": float(rng.integers(1, 40))}
+        for i in range(m):
+            if rng.random() < 0.7:
+                v[f"c{i}"] = float(rng.integers(1, 12))
+        vars_[f"x{j}"] = v
+    model = {"optimize": "obj", "opType": "max", "constraints": cons, "variables": vars_}
+    if integer:
+        model["ints"] = {f"x{j}": 1 for j in range(n) if rng.random() < 0.6}
+    return model
+
+
+def _scipy_solve(model):
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    names = list(model["variables"])
+    c = -np.array([model["variables"][v].get("obj", 0.0) for v in names])   # milp minimises
+    rows, lo, hi = [], [], []
+    for cname, spec in model["constraints"].items():
+        rows.append([model["variables"][v].get(cname, 0.0) for v in names])
+        lo.append(spec.get("min", -np.inf))
+        hi.append(spec.get("max", np.inf))
+    integrality = np.array([1 if v in model.get("ints", {}) else 0 for v in names])
+    res = milp(c, constraints=LinearConstraint(np.array(rows), lo, hi), integrality=integrality, bounds=Bounds(0, np.inf))
+    return (res.status == 0), (-res.fun if res.status == 0 else None), res.status
+
+
+def test_oracle_optimum_equals_an_independent_solver():
+    """The oracle is pinned on the reference's own golden vectors; this adds a check against a solver that shares no code
+    or rule with either: SciPy's HiGHS (`scipy.optimize.milp`) on random bounded LPs and small MIPs -- same
+    feasibility verdict, objective within 1e-7 relative (different algorithms, so optimal VERTICES may differ)."""
+    pytest.importorskip("scipy")
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for k in range(60):
+        integer = k % 2 == 1
+        model = _random_model(rng, int(rng.integers(3, 9)), int(rng.integers(2, 7)), integer)
+        ok, val, status = _scipy_solve(model)
+        if status not in (0, 2):      # unbounded etc.: skip, the generator makes those rare
+            continue
+        res = ref_model.Solve(model, fast_cycles=True)
+        assert bool(res["feasible"]) == ok, (k, res, status)
+        if ok:
+            assert res["bounded"] and abs(res["result"] - val) <= 1e-7 * max(1.0, abs(val)), (k, res["result"], val)
+            checked += 1
+    assert checked >= 30
+
+
+def test_big_config_fixtures_agree_with_an_independent_solver():
+    """The oracle's cached optimum of BASELINE config 3 (dense 2000x2000) and of the config-5 root relaxation equals the
+    objective SciPy's HiGHS finds for the same arrays (tests/golden/make_big_golden.py stores both) to 1e-9 relative."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z3 = np.load(os.path.join(gold, "config3_dense2000.npz"))
+    z5 = np.load(os.path.join(gold, "config5_knapsack.npz"))
+    for ours, highs in ((-float(z3["evaluation"][0]), float(z3["highs_objective"])),
+                        (-float(z5["root_evaluation"][0]), float(z5["root_highs_objective"]))):
+        assert abs(ours - highs) <= 1e-9 * abs(highs), (ours, highs)
