@@ -389,6 +389,7 @@ extern "C" int jslp_tab_upload(jslp_tab *t, const double *matrix, const int32_t 
     t->nVars = t->W + t->H - 2;
     t->lastElementIndex = t->nVars;
     t->saved.valid = false;
+    t->slots.release();  // slot descriptors copy unres / intpos / sizes of the tableau they were built for
     int rc = push_desc(t);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s));

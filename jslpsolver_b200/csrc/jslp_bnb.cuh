@@ -72,7 +72,7 @@ static int eval_node_streaming(jslp_tab *t, const jslp_bnb::Branch &b, int check
 
 // ---- K3: HBM-resident node batch (jslp_slots.cuh) ---------------------------------------------
 // Largest number of slots for which every slot still runs the ping-pong step (at most 32 rows per row CTA,
-// all B * (G + 2) CTAs co-resident), capped by the option and by what keeps the tableau pairs in L2.
+// all B * (G + 2) CTAs co-resident), capped by the option and by what keeps the buffers being written in L2.
 static int slots_for(const jslp_tab *t, int rowcap, int want) {
     if (t->node_slots == 0 || want < 2) return 0;
     if (!(t->pingpong && t->lookahead && t->nOpt == 0) || t->engine == 1) return 0;

@@ -394,6 +394,8 @@ extern "C" int jslp_add_variable(jslp_tab *t, int var_index, double cost_entry, 
     CK(cudaGetLastError());
     drop_graphs(t);  // pricing parameters changed
     t->g_batch = 0;
+    t->slots.release();  // node slots are laid out for one width
+    t->saved.valid = false;  // ... and so is a saved snapshot (backup.ts restores `width` with the matrix)
     return JSLP_OK;
 }
 
@@ -419,5 +421,7 @@ extern "C" int jslp_remove_variable(jslp_tab *t, int var_index) {
     if (rc) return rc;
     drop_graphs(t);
     t->g_batch = 0;
+    t->slots.release();
+    t->saved.valid = false;
     return JSLP_OK;
 }
