@@ -355,7 +355,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     barrier()
 
     l2_gbs = l2_copy_peak(ctx, H * W * 8) if rank == 0 else None
-    mip = run_mip_leg(args, torch, dist, rank, world) if args.mip_nodes > 0 else None
+    mip = None
+    if args.mip_nodes > 0:
+        try:
+            mip = run_mip_leg(args, torch, dist, rank, world)
+        except Exception as e:  # the LP headline must not be lost to a failure of the secondary block
+            if world > 1:
+                raise           # ... but a rank that drops out of the collectives must not leave the others waiting
+            mip = {"error": f"{type(e).__name__}: {e}"}
 
     t = torch.tensor([ms, e_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([pivots, e_pivots, launches], dtype=torch.float64, device="cuda")
