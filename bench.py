@@ -171,6 +171,11 @@ def run_mip_leg(args, torch, dist, rank, world):
     r = best
     non_root = max(1, r["node_lps_all_ranks"] - world)  # every rank solves the root itself
     slot_gbs = r["slot_bytes"] / (r["slot_ms_max_rank"] * 1e-3) / 1e9 if r["slot_ms_max_rank"] > 0 else None
+    try:  # DRAM / L2 bytes per launch of the slot batch from the committed warm-cache ncu capture
+        with open(os.path.join(ROOT, "profiles", "r02_slot_batch_ncu.json")) as f:
+            slot_ncu = json.load(f)
+    except Exception:
+        slot_ncu = None
     out = {
         "workload": f"0/1 knapsack 1024 binaries x 512 constraints (root tableau 1537x1025, 12.6 MB), seed 12345, "
                     f"BASELINE.json configs[4]; Model.solve() capped at {args.mip_nodes} committed nodes (no incumbent "
@@ -188,13 +193,18 @@ def run_mip_leg(args, torch, dist, rank, world):
         "roofline": {"bound": "hbm", "kernel": "k_pivot_step<256,2,flat8> over node slots (grid (G+2) x B)",
                      "achieved": slot_gbs, "peak": peak * world, "unit": "GB/s",
                      "frac": (slot_gbs / (peak * world)) if slot_gbs else None,
+                     "traffic": slot_ncu["dram_bytes_per_launch"] if slot_ncu else None,
+                     "l2_bytes_per_launch": slot_ncu["lts_bytes_per_launch"] if slot_ncu else None,
+                     "traffic_source": slot_ncu["source"] if slot_ncu else None,
                      "timing": "total_ms = wall clock of Model.solve() between barriers, slowest rank (presolve + tableau "
                                "build in the Python host mirror = host_front_end_ms, upload, branch and cut, read-back); "
                                "branch_and_cut_ms = CUDA events around jslp_branch_and_cut (root LP + node phase + final "
                                "re-solve)",
                      "note": "algorithmic bytes of the pivots executed in node slots (16 x rows x stride each, all "
                              "ranks) / wall time of the slot-batch graphs incl. restore, cut rows, idle slot steps "
-                             "and host polls (slowest rank); the B tableau pairs exceed L2, so this one is HBM-bound"},
+                             "and host polls (slowest rank).  One launch of 5 slots moves 126 MB algorithmically; `traffic` is what "
+                             "DRAM saw per launch in the warm-cache ncu capture (reads are served from L2 thanks to the "
+                             "dead-load hint, every written line is written back once)"},
     }
     try:
         with open(os.path.join(ROOT, "profiles", f"r02_cpu_config5_cap{args.mip_nodes}.json")) as f:
