@@ -30,6 +30,8 @@ def _worker(rank, world, port, per, out_dir):
     sys.path.insert(0, ROOT)
     from jslpsolver_b200 import distributed as D
     assert D.is_active() and D.rank_and_world() == (rank, world)
+    # under gloo there is no in-library NCCL communicator: the frontier falls back to the host hook below
+    assert D.nccl_communicator(object()) is None
     cb, keep = D.make_all_gather_hook()
     ok = True
     for rnd in range(3):  # several rounds with different payload sizes, like successive B&B rounds
