@@ -619,3 +619,19 @@ def test_solve_agrees_with_an_independent_solver():
             assert res["bounded"] and abs(res["result"] - val) <= 1e-7 * max(1.0, abs(val)), (k, res["result"], val)
             checked += 1
     assert checked >= 20
+    # mixed min / max / equal rows, both senses, either sign of cost: verdicts too (HiGHS status 0 / 2 / 3)
+    from test_oracle_golden import _random_model_mixed, _scipy_solve_mixed
+    rng = np.random.default_rng(6)
+    seen = {0: 0, 2: 0, 3: 0}
+    for k in range(90):
+        model = _random_model_mixed(rng, int(rng.integers(3, 14)), int(rng.integers(2, 9)), k % 3 == 1)
+        status, val = _scipy_solve_mixed(model)
+        res = J.Solve(model)
+        if status == 0:
+            assert res["feasible"] and res["bounded"] and abs(res["result"] - val) <= 1e-7 * max(1.0, abs(val)), (k, res, val)
+        elif status == 2:
+            assert not res["feasible"], (k, res)
+        elif status == 3:
+            assert not (res["feasible"] and res["bounded"]), (k, res)
+        seen[status] = seen.get(status, 0) + 1
+    assert seen[0] >= 15 and seen[2] >= 15 and seen[3] >= 5, seen

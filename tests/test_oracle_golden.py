@@ -337,3 +337,60 @@ def test_big_config_fixtures_agree_with_an_independent_solver():
     for ours, highs in ((-float(z3["evaluation"][0]), float(z3["highs_objective"])),
                         (-float(z5["root_evaluation"][0]), float(z5["root_highs_objective"]))):
         assert abs(ours - highs) <= 1e-9 * abs(highs), (ours, highs)
+
+
+def _random_model_mixed(rng, n, m, integer):
+    """min / max / equal rows, max or min objective, costs of either sign: optimal, infeasible and unbounded instances."""
+    cons = {}
+    for i in range(m):
+        r = rng.random()
+        cons[f"c{i}"] = ({"max": float(rng.integers(5, 60))} if r < 0.5 else
+                         ({"min": float(rng.integers(5, 80))} if r < 0.85 else {"equal": float(rng.integers(5, 40))}))
+    vars_ = {}
+    for j in range(n):
+        v = {"obj": float(rng.integers(-10, 40))}
+        for i in range(m):
+            if rng.random() < 0.6:
+                v[f"c{i}"] = float(rng.integers(1, 12))
+        vars_[f"x{j}"] = v
+    model = {"optimize": "obj", "opType": "max" if rng.random() < 0.7 else "min", "constraints": cons, "variables": vars_}
+    if integer:
+        model["ints"] = {f"x{j}": 1 for j in range(n) if rng.random() < 0.5}
+    return model
+
+
+def _scipy_solve_mixed(model):
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    names = list(model["variables"])
+    sign = -1.0 if model["opType"] == "max" else 1.0
+    c = sign * np.array([model["variables"][v].get("obj", 0.0) for v in names])
+    rows, lo, hi = [], [], []
+    for cname, spec in model["constraints"].items():
+        rows.append([model["variables"][v].get(cname, 0.0) for v in names])
+        if "equal" in spec:
+            lo.append(spec["equal"]); hi.append(spec["equal"])
+        else:
+            lo.append(spec.get("min", -np.inf)); hi.append(spec.get("max", np.inf))
+    integrality = np.array([1 if v in model.get("ints", {}) else 0 for v in names])
+    res = milp(c, constraints=LinearConstraint(np.array(rows), lo, hi), integrality=integrality, bounds=Bounds(0, np.inf))
+    return res.status, (sign * res.fun if res.status == 0 else None)
+
+
+def test_oracle_verdicts_equal_an_independent_solver_on_mixed_models():
+    """Optimal / infeasible / unbounded verdicts and optimal values against SciPy's HiGHS on models with `min`, `max` and
+    `equal` rows, both objective senses, costs of either sign, LPs and MIPs (HiGHS status 0 / 2 / 3)."""
+    pytest.importorskip("scipy")
+    rng = np.random.default_rng(5)
+    seen = {0: 0, 2: 0, 3: 0}
+    for k in range(200):
+        model = _random_model_mixed(rng, int(rng.integers(3, 14)), int(rng.integers(2, 9)), k % 3 == 1)
+        status, val = _scipy_solve_mixed(model)
+        res = ref_model.Solve(model, fast_cycles=True)
+        if status == 0:
+            assert res["feasible"] and res["bounded"] and abs(res["result"] - val) <= 1e-7 * max(1.0, abs(val)), (k, res, val)
+        elif status == 2:
+            assert not res["feasible"], (k, res)
+        elif status == 3:
+            assert not (res["feasible"] and res["bounded"]), (k, res)
+        seen[status] = seen.get(status, 0) + 1
+    assert seen[0] >= 40 and seen[2] >= 40 and seen[3] >= 15, seen
