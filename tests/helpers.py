@@ -48,3 +48,28 @@ def strip_timeouts(model: dict) -> dict:
     if isinstance(m.get("options"), dict):
         m["options"].pop("timeout", None)
     return m
+
+
+def highs_solve(model: dict):
+    """A jsLPSolver JSON model (single objective; `min`/`max`/`equal` rows, `ints`, `binaries`) solved by SciPy's
+    HiGHS, which shares no code or pivot rule with the reference, the oracle or the CUDA path.
+    Returns (status, objective): status 0 optimal, 2 infeasible, 3 unbounded, 4 unbounded-or-infeasible (scipy.optimize.milp's codes)."""
+    import numpy as np
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    names = list(model["variables"])
+    key = model["optimize"]
+    sign = -1.0 if model["opType"] == "max" else 1.0
+    c = sign * np.array([model["variables"][v].get(key, 0.0) for v in names], dtype=float)
+    rows, lo, hi = [], [], []
+    for cname, spec in model["constraints"].items():
+        rows.append([model["variables"][v].get(cname, 0.0) for v in names])
+        if "equal" in spec:
+            lo.append(spec["equal"]); hi.append(spec["equal"])
+        else:
+            lo.append(spec.get("min", -np.inf)); hi.append(spec.get("max", np.inf))
+    ints, bins = model.get("ints", {}), model.get("binaries", {})
+    integrality = np.array([1 if (v in ints or v in bins) else 0 for v in names])
+    upper = np.array([1.0 if v in bins else np.inf for v in names])
+    res = milp(c, constraints=LinearConstraint(np.array(rows, dtype=float), lo, hi), integrality=integrality,
+               bounds=Bounds(0, upper))
+    return res.status, (sign * res.fun if res.status == 0 else None)
