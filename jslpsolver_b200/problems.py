@@ -91,7 +91,7 @@ def knapsack_mip_model(n_items: int, n_cons: int, seed: int = 12345, tolerance: 
 
 # ---- the reference's stress families (solver.stress.test.ts:41-215 solves them at 10..50 variables) ----------
 # Same shapes and distributions as problem-generator.ts's families, drawn from numpy's stream; every model is a
-# plain jsLPSolver JSON dict, so the oracle, the GPU path and an outside solver all see the same instance.
+# plain jsLPSolver JSON dict, so every implementation that is compared (and an outside solver) sees the same instance.
 
 def _sparse_columns(rng, names, rows, density, lo, hi):
     """variables[name][row] = U{lo..hi} wherever a Bernoulli(density) mask is set."""
